@@ -1,0 +1,320 @@
+"""bflk -- Python host binding (ctypes) of the B200-native delay-and-sum library.
+
+The product is ``libbflk.so`` (CUDA kernels for sm_100a behind the C ABI in ``include/bflk.h``); this
+module only marshals numpy / torch buffers into that ABI.  There is no CPU fallback: if the shared
+library is missing or no B200 is visible, construction raises.
+
+Class names mirror the reference's workers (src/dsp/mimo.h, src/dsp/miso.h): ``MIMOWorker`` produces
+the full-grid power map, ``MISOWorker`` the dynamically steered audio + beam power.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libbflk.so")
+
+N_SAMPLES = 256       # src/fpga/streams.hpp:28
+WINDOW = 1024         # N_ITEMS_BUFFER, src/fpga/streams.hpp:30-32
+ELEMENTS = 64         # src/geometry/antenna.h:20
+SAMPLE_RATE = 48828.0
+PROPAGATION_SPEED = 340.0
+
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2
+
+# every symbol include/bflk.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "bflk_default_config", "bflk_version", "bflk_create", "bflk_destroy", "bflk_last_error",
+    "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
+    "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_direction_range", "bflk_get_n_directions",
+    "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_batch",
+    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_launch_count", "bflk_miso", "bflk_miso_dev",
+    "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("n_channels", C.c_int32), ("frame_len", C.c_int32), ("history", C.c_int32),
+                ("window_len", C.c_int32), ("sample_rate", C.c_double), ("propagation_speed", C.c_double),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BflkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bflk error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Load libbflk.so (fails loudly when the CUDA extension has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with beamforming-lk_b200/build.sh "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+    L.bflk_default_config.argtypes = [C.POINTER(Config)]
+    L.bflk_default_config.restype = None
+    L.bflk_version.restype = C.c_int
+    L.bflk_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.bflk_destroy.argtypes = [vp]
+    L.bflk_last_error.argtypes = [vp]
+    L.bflk_last_error.restype = C.c_char_p
+    L.bflk_set_geometry.argtypes = [vp, vp, i32]
+    L.bflk_set_tiled_geometry.argtypes = [vp, i32, vp]
+    L.bflk_get_geometry.argtypes = [vp, vp]
+    L.bflk_set_channel_mask.argtypes = [vp, vp, i32]
+    L.bflk_set_grid_fov.argtypes = [vp, i32, i32, f32]
+    L.bflk_set_grid_tables.argtypes = [vp, vp, vp, i32]
+    L.bflk_set_direction_range.argtypes = [vp, i32, i32]
+    L.bflk_get_n_directions.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.bflk_get_grid.argtypes = [vp, vp, vp]
+    L.bflk_get_tables.argtypes = [vp, vp, vp]
+    L.bflk_steer_tables.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bflk_power_map.argtypes = [vp, vp, vp]
+    L.bflk_power_map_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_set_kernel.argtypes = [vp, i32]
+    L.bflk_launch_count.argtypes = [vp]
+    L.bflk_launch_count.restype = i64
+    L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.bflk_miso_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+    L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
+    L.bflk_calibrate.argtypes = [vp, vp, i32, f32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
+    L.bflk_ingest_i32.argtypes = [vp, vp, i32, i32, vp]
+    _lib = L
+    return L
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def tile_origins(nx, ny, pitch=0.16):
+    """Origins of nx x ny abutting 8x8 arrays (0.16 m pitch), centred, row-major: tile a = j*nx + i."""
+    o = [[(i - (nx - 1) / 2) * pitch, (j - (ny - 1) / 2) * pitch, 0.0] for j in range(ny) for i in range(nx)]
+    return np.asarray(o, np.float32)
+
+
+class Beamformer:
+    """Thin object wrapper over a ``bflk_handle``."""
+
+    def __init__(self, n_channels=ELEMENTS, frame_len=N_SAMPLES, history=N_SAMPLES, window_len=WINDOW,
+                 sample_rate=SAMPLE_RATE, propagation_speed=PROPAGATION_SPEED, device=0):
+        self._L = load_library()
+        cfg = Config()
+        self._L.bflk_default_config(C.byref(cfg))
+        cfg.n_channels, cfg.frame_len, cfg.history, cfg.window_len = n_channels, frame_len, history, window_len
+        cfg.sample_rate, cfg.propagation_speed, cfg.device = sample_rate, propagation_speed, device
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._L.bflk_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise BflkError(rc, self._L.bflk_last_error(None).decode())
+
+    # -- plumbing -----------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise BflkError(rc, self._L.bflk_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.bflk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_channels(self):
+        return self.cfg.n_channels
+
+    @property
+    def frame_len(self):
+        return self.cfg.frame_len
+
+    def launch_count(self):
+        return int(self._L.bflk_launch_count(self._h))
+
+    # -- geometry / tables ------------------------------------------------------------------------------------
+    def set_geometry(self, xyz):
+        xyz = _np(xyz, np.float32).reshape(-1, 3)
+        self._check(self._L.bflk_set_geometry(self._h, _ptr(xyz), xyz.shape[0]))
+
+    def set_tiled_geometry(self, origins):
+        origins = _np(origins, np.float32).reshape(-1, 3)
+        self._check(self._L.bflk_set_tiled_geometry(self._h, origins.shape[0], _ptr(origins)))
+
+    def geometry(self):
+        xyz = np.zeros((self.n_channels, 3), np.float32)
+        self._check(self._L.bflk_get_geometry(self._h, _ptr(xyz)))
+        return xyz
+
+    def set_channel_mask(self, index=None):
+        if index is None:
+            self._check(self._L.bflk_set_channel_mask(self._h, None, 0))
+        else:
+            index = _np(index, np.int32)
+            self._check(self._L.bflk_set_channel_mask(self._h, _ptr(index), index.shape[0]))
+
+    def set_grid_fov(self, rows, cols, fov_deg):
+        self._check(self._L.bflk_set_grid_fov(self._h, rows, cols, float(fov_deg)))
+
+    def set_grid_tables(self, offsets, fractions):
+        offsets, fractions = _np(offsets, np.int32), _np(fractions, np.float32)
+        assert offsets.shape == fractions.shape and offsets.shape[1] == self.n_channels
+        self._check(self._L.bflk_set_grid_tables(self._h, _ptr(offsets), _ptr(fractions), offsets.shape[0]))
+
+    def set_direction_range(self, first, count):
+        self._check(self._L.bflk_set_direction_range(self._h, first, count))
+
+    def n_directions(self):
+        t, f, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._L.bflk_get_n_directions(self._h, C.byref(t), C.byref(f), C.byref(c)))
+        return t.value, f.value, c.value
+
+    def grid(self):
+        D = self.n_directions()[0]
+        th, ph = np.zeros(D, np.float64), np.zeros(D, np.float64)
+        self._check(self._L.bflk_get_grid(self._h, _ptr(th), _ptr(ph)))
+        return th, ph
+
+    def tables(self):
+        D = self.n_directions()[0]
+        off = np.zeros((D, self.n_channels), np.int32)
+        fr = np.zeros((D, self.n_channels), np.float32)
+        self._check(self._L.bflk_get_tables(self._h, _ptr(off), _ptr(fr)))
+        return off, fr
+
+    def steer_tables(self, theta, phi):
+        theta, phi = _np(theta, np.float64).ravel(), _np(phi, np.float64).ravel()
+        T = theta.shape[0]
+        off = np.zeros((T, self.n_channels), np.int32)
+        fr = np.zeros((T, self.n_channels), np.float32)
+        self._check(self._L.bflk_steer_tables(self._h, _ptr(theta), _ptr(phi), T, _ptr(off), _ptr(fr)))
+        return off, fr
+
+    def set_kernel(self, which):
+        self._check(self._L.bflk_set_kernel(self._h, which))
+
+    # -- hot path -----------------------------------------------------------------------------------------------
+    def power_map(self, window):
+        """window [C][W] float32 (host) -> power [count] (MIMOWorker::update)."""
+        window = _np(window, np.float32)
+        assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
+        out = np.zeros(self.n_directions()[2], np.float32)
+        self._check(self._L.bflk_power_map(self._h, _ptr(window), _ptr(out)))
+        return out
+
+    def power_map_batch(self, stream, n_frames):
+        """stream [C][T] float32 (host), frame b at sample b*N -> power [B][count]."""
+        stream = _np(stream, np.float32)
+        assert stream.shape[0] == self.n_channels
+        out = np.zeros((n_frames, self.n_directions()[2]), np.float32)
+        self._check(self._L.bflk_power_map_batch(self._h, _ptr(stream), stream.shape[1], n_frames, _ptr(out)))
+        return out
+
+    def power_map_batch_ptr(self, stream_ptr, n_samples, n_frames, power_ptr, cuda_stream=0):
+        """Raw host-pointer variant (pinned buffers) -- what bench.py's e2e leg calls."""
+        self._check(self._L.bflk_power_map_batch(self._h, C.c_void_p(stream_ptr), n_samples, n_frames, C.c_void_p(power_ptr)))
+
+    def power_map_batch_dev(self, stream_dev_ptr, n_samples, n_frames, power_dev_ptr, cuda_stream=0):
+        """Device pointers (e.g. torch tensors' data_ptr()), asynchronous on cuda_stream."""
+        self._check(self._L.bflk_power_map_batch_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
+                                                     C.c_void_p(power_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def miso(self, theta, phi, window, want_audio=True, want_power=True):
+        """Particle::steer + das + beam for T targets: returns (audio [T][N] | None, power [T] | None)."""
+        theta, phi = _np(theta, np.float64).ravel(), _np(phi, np.float64).ravel()
+        window = _np(window, np.float32)
+        assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
+        T = theta.shape[0]
+        audio = np.zeros((T, self.frame_len), np.float32) if want_audio else None
+        power = np.zeros(T, np.float32) if want_power else None
+        self._check(self._L.bflk_miso(self._h, _ptr(theta), _ptr(phi), T, _ptr(window),
+                                      _ptr(audio) if want_audio else None, _ptr(power) if want_power else None))
+        return audio, power
+
+    # -- neighbours ---------------------------------------------------------------------------------------------
+    def heatmap(self, power):
+        power = _np(power, np.float32).ravel()
+        heat = np.zeros(power.shape[0], np.uint8)
+        arg, mx = C.c_int32(), C.c_float()
+        self._check(self._L.bflk_heatmap(self._h, _ptr(power), power.shape[0], _ptr(heat), C.byref(arg), C.byref(mx)))
+        return heat, arg.value, mx.value
+
+    def calibrate(self, signals, reference_power_level=1e-5):
+        signals = _np(signals, np.float32)
+        assert signals.shape[0] == ELEMENTS
+        index = np.zeros(ELEMENTS, np.int32)
+        corr = np.zeros(ELEMENTS, np.float32)
+        n, med, mean = C.c_int32(), C.c_float(), C.c_float()
+        self._check(self._L.bflk_calibrate(self._h, _ptr(signals), signals.shape[1], reference_power_level,
+                                           _ptr(index), _ptr(corr), C.byref(n), C.byref(med), C.byref(mean)))
+        return index[:n.value].copy(), corr[:n.value].copy(), med.value, mean.value
+
+    def ingest_i32(self, frames):
+        frames = _np(frames, np.int32)
+        n, ns = frames.shape
+        out = np.zeros((ns, n), np.float32)
+        self._check(self._L.bflk_ingest_i32(self._h, _ptr(frames), n, ns, _ptr(out)))
+        return out
+
+
+class MIMOWorker(Beamformer):
+    """Full-grid power map, constructor arguments as MIMOWorker(pipeline, antenna, running, rows, columns, fov)
+    (src/dsp/mimo.h:36) with the antenna given as tile origins."""
+
+    def __init__(self, origins, rows, columns, fov, index=None, device=0, **kw):
+        origins = np.asarray(origins, np.float32).reshape(-1, 3)
+        super().__init__(n_channels=ELEMENTS * origins.shape[0], device=device, **kw)
+        self.set_tiled_geometry(origins)
+        if index is not None:
+            self.set_channel_mask(index)
+        self.rows, self.columns, self.fov = rows, columns, fov
+        self.set_grid_fov(rows, columns, fov)
+        self.powerdB = np.zeros(rows * columns, np.float32)
+
+    def update(self, window):
+        """MIMOWorker::update (src/dsp/mimo.cpp:97-151) on a [C][W] snapshot."""
+        self.powerdB = self.power_map(window)
+        return self.powerdB
+
+    def populateHeatmap(self):
+        """MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95): uint8 [rows][columns]."""
+        heat, arg, mx = self.heatmap(self.powerdB)
+        return heat.reshape(self.rows, self.columns), arg, mx
+
+
+class MISOWorker(Beamformer):
+    """Dynamically steered DAS, MISOWorker(pipeline, antenna, running, fov) (src/dsp/miso.h:18), T targets."""
+
+    def __init__(self, origins, fov=180.0, index=None, device=0, **kw):
+        origins = np.asarray(origins, np.float32).reshape(-1, 3)
+        super().__init__(n_channels=ELEMENTS * origins.shape[0], device=device, **kw)
+        self.set_tiled_geometry(origins)
+        if index is not None:
+            self.set_channel_mask(index)
+        self.fov = fov
+        self.theta = np.zeros(1)
+        self.phi = np.zeros(1)
+
+    def steer(self, theta, phi):
+        self.theta, self.phi = np.atleast_1d(theta).astype(np.float64), np.atleast_1d(phi).astype(np.float64)
+
+    def update(self, window):
+        """beamformer.steer(direction); beamformer.das(data) (src/dsp/miso.cpp:42-46) for every target."""
+        return self.miso(self.theta, self.phi, window)

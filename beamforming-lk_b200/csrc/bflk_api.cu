@@ -1,0 +1,607 @@
+// bflk_api.cu -- the C ABI declared in include/bflk.h: host-side logic + kernel dispatch.
+//
+// Host work kept here on purpose (it is O(D) or O(C), one-time, and needs libm in double exactly like
+// the reference): the direction grid of MIMOWorker::computeDelayLUT (src/dsp/mimo.cpp:20-43), the
+// rotation-matrix entries of rotateZ / rotateY (src/geometry/geometry.cpp:219-233), create_antenna
+// (src/geometry/antenna.cpp:60-87) and the median gate of AWProcessingUnit::calibrate
+// (src/aw_processing_unit/aw_processing_unit.cpp:148-200).  Everything O(D*C) or larger runs on the GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "bflk_internal.h"
+
+using namespace bflk;
+
+static thread_local std::string g_create_error;
+
+static int create_fail(int code, const std::string &msg) {
+    g_create_error = msg;
+    return code;
+}
+
+extern "C" {
+
+int bflk_version(void) { return BFLK_VERSION; }
+
+void bflk_default_config(bflk_config *cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->n_channels = 64;
+    cfg->frame_len = 256;
+    cfg->history = 256;
+    cfg->window_len = 1024;
+    cfg->sample_rate = 48828.0;
+    cfg->propagation_speed = 340.0;
+    cfg->device = 0;
+}
+
+const char *bflk_last_error(const bflk_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int bflk_create(const bflk_config *cfg, bflk_handle **out) {
+    if (!cfg || !out) return create_fail(BFLK_ERR_INVALID, "bflk_create: null argument");
+    *out = nullptr;
+    if (cfg->n_channels <= 0 || cfg->frame_len < 3 || cfg->history < 0 || cfg->window_len < cfg->frame_len + 1 ||
+        !(cfg->sample_rate > 0) || !(cfg->propagation_speed > 0))
+        return create_fail(BFLK_ERR_INVALID, "bflk_create: invalid configuration");
+    if (cfg->history + cfg->frame_len + 1 > cfg->window_len)
+        return create_fail(BFLK_ERR_INVALID, "bflk_create: window_len must be >= history + frame_len + 1");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0)
+        return create_fail(BFLK_ERR_NO_DEVICE, std::string("bflk_create: no CUDA device (") + cudaGetErrorString(e) +
+                                                   "); this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= n_dev) return create_fail(BFLK_ERR_INVALID, "bflk_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+        return create_fail(BFLK_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return create_fail(BFLK_ERR_NO_DEVICE, "bflk_create: device is not sm_100 (kernels are built for sm_100a only)");
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess)
+        return create_fail(BFLK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    bflk_handle *h = new bflk_handle();
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return create_fail(BFLK_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return BFLK_OK;
+}
+
+int bflk_destroy(bflk_handle *h) {
+    if (!h) return BFLK_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) {
+        cudaStreamSynchronize(h->stream);
+        cudaStreamDestroy(h->stream);
+    }
+    h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
+    h->d_tile_dirs.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
+    h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
+    h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release();
+    delete h;
+    return BFLK_OK;
+}
+
+// ---- geometry -----------------------------------------------------------------------------------------
+static void invalidate_tables(bflk_handle *h) {
+    h->have_grid = false;
+    h->tiles_valid = false;
+    h->n_dir = 0;
+    h->dir_first = h->dir_count = 0;
+}
+
+int bflk_set_geometry(bflk_handle *h, const float *xyz, int32_t n_channels) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!xyz || n_channels != h->cfg.n_channels)
+        return h->fail(BFLK_ERR_INVALID, "bflk_set_geometry: expected %d channels, got %d", h->cfg.n_channels, n_channels);
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->xyz.assign(xyz, xyz + 3 * (size_t)n_channels);
+    BFLK_CUDA(h, h->d_xyz.reserve(3 * (size_t)n_channels));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_xyz.p, h->xyz.data(), h->xyz.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_geometry = true;
+    invalidate_tables(h);
+    if (h->index.empty()) return bflk_set_channel_mask(h, nullptr, 0);
+    return BFLK_OK;
+}
+
+int bflk_set_tiled_geometry(bflk_handle *h, int32_t n_tiles, const float *origins) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (n_tiles <= 0 || !origins || n_tiles * 64 != h->cfg.n_channels)
+        return h->fail(BFLK_ERR_INVALID, "bflk_set_tiled_geometry: n_tiles*64 must equal n_channels (%d)", h->cfg.n_channels);
+    // create_antenna(position, COLUMNS = 8, ROWS = 8, DISTANCE = 0.02f), antenna.cpp:60-76
+    const int columns = 8, rows = 8;
+    const float distance = 0.02f;
+    const float half = distance / 2;
+    std::vector<float> xyz(3 * (size_t)h->cfg.n_channels);
+    for (int a = 0; a < n_tiles; a++) {
+        int i = 0;
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < columns; c++, i++) {
+                float *p = &xyz[3 * ((size_t)a * 64 + i)];
+                p[0] = (static_cast<float>(c) * distance - rows * half + half) + origins[3 * a + 0];
+                p[1] = (static_cast<float>(r) * distance - columns * half + half) + origins[3 * a + 1];
+                p[2] = 0.f + origins[3 * a + 2];
+            }
+    }
+    return bflk_set_geometry(h, xyz.data(), h->cfg.n_channels);
+}
+
+int bflk_get_geometry(const bflk_handle *h, float *xyz) {
+    if (!h || !xyz || !h->have_geometry) return BFLK_ERR_STATE;
+    std::memcpy(xyz, h->xyz.data(), h->xyz.size() * sizeof(float));
+    return BFLK_OK;
+}
+
+int bflk_set_channel_mask(bflk_handle *h, const int32_t *index, int32_t usable) {
+    if (!h) return BFLK_ERR_INVALID;
+    const int C = h->cfg.n_channels;
+    std::vector<int32_t> idx;
+    if (!index) {
+        idx.resize(C);
+        for (int c = 0; c < C; c++) idx[c] = c;
+    } else {
+        if (usable <= 0 || usable > C) return h->fail(BFLK_ERR_INVALID, "bflk_set_channel_mask: usable=%d out of range", usable);
+        idx.assign(index, index + usable);
+        for (int v : idx)
+            if (v < 0 || v >= C) return h->fail(BFLK_ERR_INVALID, "bflk_set_channel_mask: channel %d out of range", v);
+    }
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->index = idx;
+    BFLK_CUDA(h, h->d_index.reserve(idx.size()));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_index.p, h->index.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->tiles_valid = false;
+    return BFLK_OK;
+}
+
+// ---- steering tables ------------------------------------------------------------------------------------
+static DirTrig make_trig(double theta, double phi) {
+    // steer(): rotateY(-static_cast<float>(theta)) * (rotateZ(static_cast<float>(phi)) * points), antenna.cpp:103
+    const float az = static_cast<float>(phi);
+    const float ay = -static_cast<float>(theta);
+    DirTrig t;
+    t.cz = static_cast<float>(std::cos((double)az));
+    t.sz = static_cast<float>(std::sin((double)az));
+    t.cy = static_cast<float>(std::cos((double)ay));
+    t.sy = static_cast<float>(std::sin((double)ay));
+    return t;
+}
+
+static float delay_scale(const bflk_handle *h) { return (float)(h->cfg.sample_rate / h->cfg.propagation_speed); }
+
+// Runs the device table kernel for n directions; results land in d_off/d_frac; *max_delay updated.
+static int run_steer_tables(bflk_handle *h, const double *theta, const double *phi, int n, int32_t *d_off, float *d_frac,
+                            int32_t *max_delay) {
+    BFLK_CUDA(h, h->p_trig.reserve(n));
+    BFLK_CUDA(h, h->d_trig.reserve(n));
+    BFLK_CUDA(h, h->d_misc.reserve(4));
+    BFLK_CUDA(h, h->p_misc.reserve(4));
+    for (int i = 0; i < n; i++) h->p_trig.p[i] = make_trig(theta[i], phi[i]);
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_trig.p, h->p_trig.p, n * sizeof(DirTrig), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
+    BFLK_CUDA(h, launch_steer_tables(h->d_trig.p, n, h->d_xyz.p, h->cfg.n_channels, delay_scale(h), h->cfg.history, d_off,
+                                     d_frac, h->d_misc.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    *max_delay = h->p_misc.p[0];
+    return BFLK_OK;
+}
+
+static int check_delay_range(bflk_handle *h, int max_delay, const char *who) {
+    if (max_delay > h->cfg.history)
+        return h->fail(BFLK_ERR_RANGE, "%s: largest delay %d samples exceeds history %d", who, max_delay, h->cfg.history);
+    return BFLK_OK;
+}
+
+int bflk_set_grid_fov(bflk_handle *h, int32_t rows, int32_t cols, float fov_deg) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_geometry) return h->fail(BFLK_ERR_STATE, "bflk_set_grid_fov: set the geometry first");
+    if (rows <= 0 || cols <= 0 || !(fov_deg > 0.f) || fov_deg > 180.f)
+        return h->fail(BFLK_ERR_INVALID, "bflk_set_grid_fov: invalid grid %d x %d fov %g", rows, cols, (double)fov_deg);
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int D = rows * cols;
+    std::vector<double> theta(D), phi(D);
+    // MIMOWorker::computeDelayLUT grid, mimo.cpp:21-43 (all double)
+    const double fovRadian = (double)fov_deg * (M_PI / 180.0);
+    const double separationRows = std::sin(fovRadian / 2.0) / (static_cast<double>(rows) / 2.0);
+    const double separationColumns = std::sin(fovRadian / 2.0) / (static_cast<double>(cols) / 2.0);
+    int k = 0;
+    for (int r = 0; r < rows; r++) {
+        for (int c = 0; c < cols; c++, k++) {
+            double y = static_cast<double>(r) * separationRows - static_cast<double>(rows) * separationRows / 2.0 + separationRows / 2.0;
+            double x = static_cast<double>(c) * separationColumns - static_cast<double>(cols) * separationColumns / 2.0 + separationColumns / 2.0;
+            double norm = std::sqrt(std::pow(x, 2) + std::pow(y, 2));
+            if (norm == 0.0) {  // centre cell of an odd grid: the reference divides by zero; defined as boresight
+                theta[k] = 0.0;
+                phi[k] = 0.0;
+                continue;
+            }
+            x /= norm;
+            y /= norm;
+            if (norm > 1.0) norm = 1.0;
+            theta[k] = std::asin(norm);
+            phi[k] = std::atan2(y, x);
+        }
+    }
+    const size_t DC = (size_t)D * h->cfg.n_channels;
+    BFLK_CUDA(h, h->d_off.reserve(DC));
+    BFLK_CUDA(h, h->d_frac.reserve(DC));
+    int32_t max_delay = 0;
+    int rc = run_steer_tables(h, theta.data(), phi.data(), D, h->d_off.p, h->d_frac.p, &max_delay);
+    if (rc) return rc;
+    invalidate_tables(h);
+    if ((rc = check_delay_range(h, max_delay, "bflk_set_grid_fov"))) return rc;
+    h->theta.swap(theta);
+    h->phi.swap(phi);
+    h->rows = rows;
+    h->cols = cols;
+    h->n_dir = D;
+    h->dir_first = 0;
+    h->dir_count = D;
+    h->max_delay = max_delay;
+    h->have_grid = true;
+    return BFLK_OK;
+}
+
+int bflk_set_grid_tables(bflk_handle *h, const int32_t *offsets, const float *fractions, int32_t n_directions) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!offsets || !fractions || n_directions <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_set_grid_tables: null / empty tables");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t DC = (size_t)n_directions * h->cfg.n_channels;
+    BFLK_CUDA(h, h->d_off.reserve(DC));
+    BFLK_CUDA(h, h->d_frac.reserve(DC));
+    BFLK_CUDA(h, h->d_misc.reserve(4));
+    BFLK_CUDA(h, h->p_misc.reserve(4));
+    invalidate_tables(h);
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_off.p, offsets, DC * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_frac.p, fractions, DC * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->p_misc.p[0] = INT32_MIN;
+    h->p_misc.p[1] = INT32_MAX;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_misc.p, h->p_misc.p, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_offset_range(h->d_off.p, DC, h->d_misc.p, h->d_misc.p + 1, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int max_off = h->p_misc.p[0], min_off = h->p_misc.p[1];
+    if (min_off < 0 || max_off > h->cfg.history)
+        return h->fail(BFLK_ERR_RANGE, "bflk_set_grid_tables: offsets must lie in [0, history = %d]; got [%d, %d]",
+                       h->cfg.history, min_off, max_off);
+    const int max_delay = h->cfg.history - min_off;
+    h->theta.clear();
+    h->phi.clear();
+    h->rows = h->cols = 0;
+    h->n_dir = n_directions;
+    h->dir_first = 0;
+    h->dir_count = n_directions;
+    h->max_delay = max_delay;
+    h->have_grid = true;
+    return BFLK_OK;
+}
+
+int bflk_set_direction_range(bflk_handle *h, int32_t first, int32_t count) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_set_direction_range: set the grid first");
+    if (first < 0 || count <= 0 || first + count > h->n_dir)
+        return h->fail(BFLK_ERR_INVALID, "bflk_set_direction_range: [%d, %d) outside grid of %d", first, first + count, h->n_dir);
+    h->dir_first = first;
+    h->dir_count = count;
+    h->tiles_valid = false;
+    return BFLK_OK;
+}
+
+int bflk_get_n_directions(const bflk_handle *h, int32_t *total, int32_t *first, int32_t *count) {
+    if (!h || !h->have_grid) return BFLK_ERR_STATE;
+    if (total) *total = h->n_dir;
+    if (first) *first = h->dir_first;
+    if (count) *count = h->dir_count;
+    return BFLK_OK;
+}
+
+int bflk_get_grid(const bflk_handle *h, double *theta, double *phi) {
+    if (!h || !h->have_grid || h->theta.empty()) return BFLK_ERR_STATE;
+    if (theta) std::memcpy(theta, h->theta.data(), h->theta.size() * sizeof(double));
+    if (phi) std::memcpy(phi, h->phi.data(), h->phi.size() * sizeof(double));
+    return BFLK_OK;
+}
+
+int bflk_get_tables(const bflk_handle *hc, int32_t *offsets, float *fractions) {
+    bflk_handle *h = const_cast<bflk_handle *>(hc);
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_get_tables: no grid");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t DC = (size_t)h->n_dir * h->cfg.n_channels;
+    if (offsets) BFLK_CUDA(h, cudaMemcpyAsync(offsets, h->d_off.p, DC * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (fractions) BFLK_CUDA(h, cudaMemcpyAsync(fractions, h->d_frac.p, DC * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+int bflk_steer_tables(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, int32_t *offsets,
+                      float *fractions) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_geometry) return h->fail(BFLK_ERR_STATE, "bflk_steer_tables: set the geometry first");
+    if (!theta || !phi || n_targets <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_steer_tables: null / empty direction list");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t TC = (size_t)n_targets * h->cfg.n_channels;
+    BFLK_CUDA(h, h->d_soff.reserve(TC));
+    BFLK_CUDA(h, h->d_sfrac.reserve(TC));
+    int32_t max_delay = 0;
+    int rc = run_steer_tables(h, theta, phi, n_targets, h->d_soff.p, h->d_sfrac.p, &max_delay);
+    if (rc) return rc;
+    if (offsets) BFLK_CUDA(h, cudaMemcpyAsync(offsets, h->d_soff.p, TC * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (fractions) BFLK_CUDA(h, cudaMemcpyAsync(fractions, h->d_sfrac.p, TC * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return check_delay_range(h, max_delay, "bflk_steer_tables");
+}
+
+// ---- power map ---------------------------------------------------------------------------------------------
+int bflk_set_kernel(bflk_handle *h, int32_t which) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (which < 0 || which > 2) return h->fail(BFLK_ERR_INVALID, "bflk_set_kernel: %d", which);
+    h->kernel_choice = which;
+    return BFLK_OK;
+}
+
+int64_t bflk_launch_count(const bflk_handle *h) { return h ? h->launches : 0; }
+
+static int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
+    return (int64_t)(n_frames - 1) * h->cfg.frame_len + h->cfg.history + h->cfg.frame_len + 1;
+}
+
+// Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.
+static int ensure_tiles(bflk_handle *h) {
+    if (h->tiles_valid) return BFLK_OK;
+    h->tiles_valid = true;
+    h->tiles_usable = false;
+    if (h->rows <= 0 || h->cols <= 0) return BFLK_OK;  // caller-supplied LUT: no grid structure to tile
+    const int cols = h->cols;
+    const int row0 = (h->dir_first / cols) & ~1;
+    const int row1 = (h->dir_first + h->dir_count - 1) / cols;  // inclusive
+    const int tile_rows = (row1 - row0) / 2 + 1, tile_cols = (cols + 1) / 2;
+    const int n_tiles = tile_rows * tile_cols;
+    const int usable = (int)h->index.size();
+    BFLK_CUDA(h, h->d_tiles.reserve((size_t)n_tiles * usable));
+    BFLK_CUDA(h, h->d_tile_dirs.reserve((size_t)n_tiles * 4));
+    BFLK_CUDA(h, h->d_misc.reserve(4));
+    BFLK_CUDA(h, h->p_misc.reserve(4));
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
+    BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
+                                    h->dir_first, h->dir_count, h->d_tiles.p, h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_tiles = n_tiles;
+    h->tile_smax = h->p_misc.p[0];
+    h->tiles_usable = h->tile_smax <= das_tile_max_span();
+    return BFLK_OK;
+}
+
+int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                             float *power_dev, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
+    if (!stream_dev || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    if (n_samples < min_stream_samples(h, n_frames))
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
+                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const int N = h->cfg.frame_len, C = h->cfg.n_channels, usable = (int)h->index.size();
+    const float norm = static_cast<float>(N * usable);  // power /= float(N_SAMPLES * count), mimo.cpp:137
+    bool tiled = false;
+    if (h->kernel_choice != 1) {
+        int rc = ensure_tiles(h);
+        if (rc) return rc;
+        tiled = h->tiles_usable;
+        if (h->kernel_choice == 2 && !tiled)
+            return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
+                           h->tile_smax, das_tile_max_span());
+    }
+    if (tiled) {
+        TileArgs a{};
+        a.stream = stream_dev;
+        a.row_stride = n_samples;
+        a.n_frames = n_frames;
+        a.frame_len = N;
+        a.frame_stride = N;
+        a.tiles = h->d_tiles.p;
+        a.tile_dirs = h->d_tile_dirs.p;
+        a.n_tiles = h->n_tiles;
+        a.usable = usable;
+        a.n_dir = h->dir_count;
+        a.min_base = h->cfg.history - h->max_delay;
+        a.max_reach = h->cfg.history;
+        a.power = power_dev;
+        a.norm = norm;
+        a.smax = h->tile_smax;
+        const int blocks_per_frame = N <= 256 ? 1 : (N - 2 + 253) / 254;
+        if (blocks_per_frame > 1) {
+            BFLK_CUDA(h, h->d_partial.reserve((size_t)n_frames * blocks_per_frame * h->dir_count));
+            a.partial = h->d_partial.p;
+        }
+        int launches = 0;
+        BFLK_CUDA(h, launch_das_tile(a, h->sm_count, st, &launches));
+        h->launches += launches;
+    } else {
+        GenericArgs a{};
+        a.stream = stream_dev;
+        a.row_stride = n_samples;
+        a.n_frames = n_frames;
+        a.frame_len = N;
+        a.frame_stride = N;
+        a.off = h->d_off.p + (size_t)h->dir_first * C;
+        a.frac = h->d_frac.p + (size_t)h->dir_first * C;
+        a.C = C;
+        a.index = h->d_index.p;
+        a.usable = usable;
+        a.n_dir = h->dir_count;
+        a.power = power_dev;
+        a.audio = nullptr;
+        a.norm = norm;
+        BFLK_CUDA(h, launch_das_generic(a, st));
+        h->launches++;
+    }
+    return BFLK_OK;
+}
+
+int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
+    if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t n_in = (size_t)h->cfg.n_channels * n_samples, n_out = (size_t)n_frames * h->dir_count;
+    BFLK_CUDA(h, h->d_window.reserve(n_in));
+    BFLK_CUDA(h, h->d_power.reserve(n_out));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, stream, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = bflk_power_map_batch_dev(h, h->d_window.p, n_samples, n_frames, h->d_power.p, h->stream);
+    if (rc) return rc;
+    BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+int bflk_power_map(bflk_handle *h, const float *window, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    return bflk_power_map_batch(h, window, h->cfg.window_len, 1, power_out);
+}
+
+// ---- MISO ---------------------------------------------------------------------------------------------------
+int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window_dev,
+                  float *audio_dev, float *power_dev, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_geometry) return h->fail(BFLK_ERR_STATE, "bflk_miso: set the geometry first");
+    if (!theta || !phi || n_targets <= 0 || !window_dev) return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int C = h->cfg.n_channels, N = h->cfg.frame_len;
+    const size_t TC = (size_t)n_targets * C;
+    BFLK_CUDA(h, h->d_soff.reserve(TC));
+    BFLK_CUDA(h, h->d_sfrac.reserve(TC));
+    int32_t max_delay = 0;
+    int rc = run_steer_tables(h, theta, phi, n_targets, h->d_soff.p, h->d_sfrac.p, &max_delay);  // Particle::steer
+    if (rc) return rc;
+    if ((rc = check_delay_range(h, max_delay, "bflk_miso"))) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    GenericArgs a{};
+    a.stream = window_dev;
+    a.row_stride = h->cfg.window_len;
+    a.n_frames = 1;
+    a.frame_len = N;
+    a.frame_stride = N;
+    a.off = h->d_soff.p;
+    a.frac = h->d_sfrac.p;
+    a.C = C;
+    a.index = h->d_index.p;
+    a.usable = (int)h->index.size();
+    a.n_dir = n_targets;
+    a.power = power_dev;
+    a.audio = audio_dev;
+    a.norm = static_cast<float>(N);  // Particle::beam: power_accumulator /= N_SAMPLES, particle.cpp:79
+    BFLK_CUDA(h, launch_das_generic(a, st));
+    h->launches++;
+    return BFLK_OK;
+}
+
+int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window,
+              float *audio_out, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!window || n_targets <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t n_in = (size_t)h->cfg.n_channels * h->cfg.window_len;
+    BFLK_CUDA(h, h->d_window.reserve(n_in));
+    BFLK_CUDA(h, h->d_audio.reserve((size_t)n_targets * h->cfg.frame_len));
+    BFLK_CUDA(h, h->d_power.reserve(n_targets));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, window, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = bflk_miso_dev(h, theta, phi, n_targets, h->d_window.p, audio_out ? h->d_audio.p : nullptr,
+                           power_out ? h->d_power.p : nullptr, h->stream);
+    if (rc) return rc;
+    if (audio_out)
+        BFLK_CUDA(h, cudaMemcpyAsync(audio_out, h->d_audio.p, (size_t)n_targets * h->cfg.frame_len * sizeof(float),
+                                     cudaMemcpyDeviceToHost, h->stream));
+    if (power_out) BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_targets * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+// ---- neighbours of the path ------------------------------------------------------------------------------------
+int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!power || n <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_heatmap: null / empty map");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    BFLK_CUDA(h, h->d_power.reserve(n));
+    BFLK_CUDA(h, h->d_misc.reserve(4 + (n + 3) / 4));
+    BFLK_CUDA(h, h->p_misc.reserve(4));
+    uint8_t *d_heat = reinterpret_cast<uint8_t *>(h->d_misc.p + 4);
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_power.p, power, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_heatmap(h->d_power.p, n, d_heat, h->d_misc.p, reinterpret_cast<float *>(h->d_misc.p + 1), h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (heat) BFLK_CUDA(h, cudaMemcpyAsync(heat, d_heat, n, cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (argmax) *argmax = h->p_misc.p[0];
+    if (maxv) std::memcpy(maxv, &h->p_misc.p[1], sizeof(float));
+    return BFLK_OK;
+}
+
+int bflk_calibrate(bflk_handle *h, const float *signals, int32_t window_len, float reference_power_level, int32_t *index,
+                   float *correction, int32_t *usable, float *median_out, float *mean_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!signals || window_len <= 0 || !index || !usable) return h->fail(BFLK_ERR_INVALID, "bflk_calibrate: null arguments");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int E = 64;  // ELEMENTS, antenna.h:20
+    BFLK_CUDA(h, h->d_window.reserve((size_t)E * window_len));
+    BFLK_CUDA(h, h->d_power.reserve(E));
+    BFLK_CUDA(h, h->p_out.reserve(E));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, signals, (size_t)E * window_len * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_channel_power(h->d_window.p, E, window_len, h->d_power.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_out.p, h->d_power.p, E * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const float *power = h->p_out.p;
+    // median gate, aw_processing_unit.cpp:144-185 (the "median" is (m[32] + m[33]) / 2 as written there)
+    float mean = 0.0f;
+    for (int s = 0; s < E; s++) mean += power[s];
+    float medians[E];
+    std::memcpy(medians, power, sizeof(medians));
+    std::sort(medians, medians + E);
+    float median = (medians[E / 2] + medians[E / 2 + 1]) / 2.0;
+    int count = 0;
+    for (int s = 0; s < E; s++) {
+        float diff = std::fabs(power[s] - median);
+        if (diff > 1e-4) {
+        } else if (power[s] < median * 1e-3) {
+        } else {
+            index[count++] = s;
+            mean += power[s];
+        }
+    }
+    mean /= static_cast<float>(count);
+    if (correction)
+        for (int s = 0; s < count; s++) correction[s] = reference_power_level / power[index[s]];
+    *usable = count;
+    if (median_out) *median_out = median;
+    if (mean_out) *mean_out = mean;
+    return BFLK_OK;
+}
+
+int bflk_ingest_i32(bflk_handle *h, const int32_t *frames, int32_t n, int32_t n_sensors, float *exposure) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!frames || !exposure || n <= 0 || n_sensors <= 0 || n_sensors % 8)
+        return h->fail(BFLK_ERR_INVALID, "bflk_ingest_i32: null buffers or n_sensors not a multiple of 8");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t cnt = (size_t)n * n_sensors;
+    BFLK_CUDA(h, h->d_misc.reserve(cnt));
+    BFLK_CUDA(h, h->d_window.reserve(cnt));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_misc.p, frames, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_ingest(h->d_misc.p, n, n_sensors, h->d_window.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(exposure, h->d_window.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+}  // extern "C"

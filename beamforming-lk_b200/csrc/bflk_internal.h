@@ -1,0 +1,195 @@
+// bflk_internal.h -- shared declarations of the B200-native DAS library (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/bflk.h"
+
+namespace bflk {
+
+// One steering direction as the device table kernel consumes it: the four rotation-matrix entries the
+// reference evaluates in double and stores as float (src/geometry/geometry.cpp:219-233).
+struct DirTrig {
+    float cz, sz;  // cos / sin of float(phi)            (rotateZ)
+    float cy, sy;  // cos / sin of -float(theta)         (rotateY)
+};
+
+// Packed per-(direction tile, usable channel) entry of the register-tiled kernel (das_tile.cu).
+// base: even-aligned smallest offset of the tile's directions, delta[r] = offset[r] - base.
+struct __align__(16) TileEntry {
+    int32_t base;       // window index of the first pair the warp loads (even)
+    uint32_t deltas;    // 4 x 8 bit: delta of direction r in bits [8r, 8r+8)
+    int32_t row;        // physical channel row in the sample stream
+    int32_t span;       // max delta (pairs of the shared window actually needed beyond K+1)
+    float frac[4];      // fractional delays of the 4 directions
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace bflk
+
+struct bflk_handle {
+    bflk_config cfg{};
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    std::string error;
+    int64_t launches = 0;
+    int kernel_choice = 0;  // 0 auto, 1 generic, 2 tiled
+
+    // geometry + mask (host copies are the source of truth; device copies feed the table kernels)
+    bool have_geometry = false;
+    std::vector<float> xyz;      // [C][3]
+    std::vector<int32_t> index;  // [usable]
+    bflk::DevBuf<float> d_xyz;
+    bflk::DevBuf<int32_t> d_index;
+
+    // steering grid
+    bool have_grid = false;
+    int32_t rows = 0, cols = 0;  // 0 x 0 when the tables were supplied by the caller
+    int32_t n_dir = 0;           // D (whole grid)
+    int32_t dir_first = 0, dir_count = 0;
+    int32_t max_delay = 0;       // largest integer delay in the LUT
+    std::vector<double> theta, phi;
+    bflk::DevBuf<int32_t> d_off;  // [D][C]
+    bflk::DevBuf<float> d_frac;   // [D][C]
+
+    // register-tiled kernel tables (built lazily for the current grid / mask / range)
+    bool tiles_valid = false;
+    bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
+    int32_t n_tiles = 0;
+    int32_t tile_smax = 0;       // compiled window slack the tables need
+    bflk::DevBuf<bflk::TileEntry> d_tiles;  // [n_tiles][usable]
+    bflk::DevBuf<int32_t> d_tile_dirs;      // [n_tiles][4] local direction index (or -1)
+
+    // scratch
+    bflk::DevBuf<float> d_window, d_power, d_audio, d_partial;
+    bflk::DevBuf<bflk::DirTrig> d_trig;
+    bflk::DevBuf<int32_t> d_soff;
+    bflk::DevBuf<float> d_sfrac;
+    bflk::DevBuf<int32_t> d_misc;
+    bflk::PinBuf<float> p_in, p_out;
+    bflk::PinBuf<bflk::DirTrig> p_trig;
+    bflk::PinBuf<int32_t> p_misc;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define BFLK_CUDA(h, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return (h)->fail(BFLK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace bflk {
+
+// ---- tables.cu --------------------------------------------------------------------------------------
+// delays -> (offset, fraction) for n_dir directions given their trig; also returns the largest integer
+// delay through d_maxdelay (device int, atomically maxed).  off / frac are [n_dir][C].
+cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d_xyz, int C, float k_scale,
+                                int history, int32_t *d_off, float *d_frac, int32_t *d_maxdelay, cudaStream_t st);
+cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st);
+// tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
+cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
+                               int rows, int cols, int first, int count, TileEntry *d_tiles, int32_t *d_tile_dirs,
+                               int n_tiles, int32_t *d_maxspan, cudaStream_t st);
+
+// ---- das_generic.cu ---------------------------------------------------------------------------------
+struct GenericArgs {
+    const float *stream;   // [C][T]
+    int64_t row_stride;    // T
+    int n_frames;          // B
+    int frame_len;         // N
+    int frame_stride;      // samples between consecutive frames' windows (N)
+    const int32_t *off;    // [n_dir][C] (already offset to the first direction)
+    const float *frac;
+    int C;
+    const int32_t *index;  // [usable]
+    int usable;
+    int n_dir;
+    float *power;          // [B][n_dir] or nullptr
+    float *audio;          // [B][n_dir][N] or nullptr
+    float norm;            // power divisor: N*count (MIMO) or N (beam)
+};
+cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st);
+
+// ---- das_tile.cu ------------------------------------------------------------------------------------
+struct TileArgs {
+    const float *stream;
+    int64_t row_stride;
+    int n_frames;
+    int frame_len;
+    int frame_stride;
+    const TileEntry *tiles;      // [n_tiles][usable]
+    const int32_t *tile_dirs;    // [n_tiles][4]
+    int n_tiles;
+    int usable;
+    int n_dir;                   // directions in this handle's range (power row length)
+    int min_base;                // smallest TileEntry::base (window start to stage)
+    int max_reach;               // largest base + span (window end to stage, in samples beyond the block)
+    float *power;                // [B][n_dir]
+    float *partial;              // [B][blocks][n_dir] when frame_len > 256
+    float norm;
+    int smax;
+};
+cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches);
+int das_tile_max_span();
+
+// ---- post.cu ----------------------------------------------------------------------------------------
+cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st);
+cudaError_t launch_channel_power(const float *d_signals, int n_ch, int W, float *d_power, cudaStream_t st);
+cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *d_exposure, cudaStream_t st);
+
+}  // namespace bflk

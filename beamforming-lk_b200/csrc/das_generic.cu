@@ -1,0 +1,71 @@
+// das_generic.cu -- delay-and-sum for an arbitrary list of directions (one CTA per direction x frame).
+//
+// This is the general path: any direction list, any channel mask, any frame length.  It serves the
+// dynamic-steering (MISO) calls -- T tracked targets, Particle::das + Particle::beam
+// (src/dsp/particle.cpp:51-103) -- and the full-grid power map (MIMOWorker::update,
+// src/dsp/mimo.cpp:97-151) when the grid does not fit the register-tiled kernel in das_tile.cu.
+//
+// Arithmetic per (direction, channel, sample) is the reference's delay() triple with every rounding
+// pinned (src/dsp/delay.cpp:24): out = out + fma(f, s[i] - s[i+1], s[i+1]), channels in mask order.
+#include "bflk_internal.h"
+
+namespace bflk {
+
+constexpr int kGenericThreads = 256;
+
+__global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArgs a) {
+    extern __shared__ float s_out[];  // [N + 2] delayed sum of this direction
+    __shared__ float s_red[kGenericThreads / 32];
+    const int d = blockIdx.x;
+    const int b = blockIdx.y;
+    const int N = a.frame_len;
+    const int32_t *off = a.off + (size_t)d * a.C;
+    const float *frac = a.frac + (size_t)d * a.C;
+    const float *base = a.stream + (size_t)b * a.frame_stride;
+
+    for (int i0 = 0; i0 < N; i0 += kGenericThreads) {
+        const int i = i0 + threadIdx.x;
+        float acc = 0.0f;
+        if (i < N) {
+            for (int s = 0; s < a.usable; s++) {
+                const int c = a.index[s];
+                const float *sig = base + (size_t)c * a.row_stride + off[c] + i;
+                const float f = frac[c];
+                const float cur = __ldg(sig), nxt = __ldg(sig + 1);
+                acc = __fadd_rn(acc, __fmaf_rn(f, __fsub_rn(cur, nxt), nxt));
+            }
+            s_out[i] = acc;
+            if (a.audio) a.audio[((size_t)b * a.n_dir + d) * N + i] = acc;
+        }
+    }
+    if (!a.power) return;
+    __syncthreads();
+    // 3-tap high-pass + mean square, mimo.cpp:131-137 / particle.cpp:68-79
+    float p = 0.0f;
+    for (int i = 1 + threadIdx.x; i < N - 1; i += kGenericThreads) {
+        float ma = __fsub_rn(__fmul_rn(s_out[i], 0.5f), __fmul_rn(0.25f, __fadd_rn(s_out[i + 1], s_out[i - 1])));
+        p = __fmaf_rn(ma, ma, p);
+    }
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < kGenericThreads / 32; w++) t += s_red[w];
+        a.power[(size_t)b * a.n_dir + d] = __fdiv_rn(t, a.norm);
+    }
+}
+
+cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st) {
+    if (a.n_dir <= 0 || a.n_frames <= 0) return cudaSuccess;
+    size_t smem = (size_t)(a.frame_len + 2) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(das_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(a.n_dir, a.n_frames);
+    das_generic_kernel<<<grid, kGenericThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace bflk

@@ -1,0 +1,104 @@
+// post.cu -- the steps either side of the delay-and-sum path.
+//   heat-map normalisation + peak  : MIMOWorker::populateHeatmap, src/dsp/mimo.cpp:61-95
+//   per-microphone power           : AWProcessingUnit::calibrate, src/aw_processing_unit/aw_processing_unit.cpp:134-146
+//   wire int32 -> float exposure   : Pipeline::receive_exposure, src/fpga/pipeline.cpp:260-297
+#include "bflk_internal.h"
+
+namespace bflk {
+
+// ---- heat-map ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) heatmap_kernel(const float *__restrict__ power, int n, uint8_t *__restrict__ heat,
+                                                      int32_t *__restrict__ argmax, float *__restrict__ maxv) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    // maxV starts at 0.0 and is replaced on strict '>' (mimo.cpp:62-69): first occurrence of the maximum
+    float best = 0.0f;
+    int besti = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = power[i];
+        if (v > best) { best = v; besti = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = besti; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? s_v[threadIdx.x] : 0.0f;
+        besti = threadIdx.x < (blockDim.x >> 5) ? s_i[threadIdx.x] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (threadIdx.x == 0) { s_v[0] = best; s_i[0] = besti == 0x7fffffff ? 0 : besti; }
+    }
+    __syncthreads();
+    const float mx = s_v[0];
+    if (threadIdx.x == 0) { *argmax = s_i[0]; *maxv = mx; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double db = (double)__fdiv_rn(power[i], mx);  // pow(powerdB[i] / maxV, 1), mimo.cpp:86
+        db *= 255.0;
+        db = db < 0.0 ? 0.0 : (db > 255.0 ? 255.0 : db);  // clip(); NaN (all-zero map) falls through to 0
+        heat[i] = (uint8_t)db;
+    }
+}
+
+cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st) {
+    heatmap_kernel<<<1, 1024, 0, st>>>(d_power, n, d_heat, d_argmax, d_max);
+    return cudaGetLastError();
+}
+
+// ---- per-channel power (calibration) --------------------------------------------------------------------
+// Sequential float accumulation per channel in sample order, as the reference loop does
+// (aw_processing_unit.cpp:136-141), so the median gate sees the same bits as the CPU restatement.
+__global__ void channel_power_kernel(const float *__restrict__ signals, int n_ch, int W, float *__restrict__ power) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) return;
+    const float *s = signals + (size_t)c * W;
+    float pv = 0.0f;
+    for (int i = 0; i < W; i++) {
+        float x = s[i];
+        pv = __fadd_rn(pv, __fmul_rn(x, x));
+    }
+    power[c] = __fdiv_rn(pv, (float)W);
+}
+
+cudaError_t launch_channel_power(const float *d_signals, int n_ch, int W, float *d_power, cudaStream_t st) {
+    channel_power_kernel<<<(n_ch + 31) / 32, 32, 0, st>>>(d_signals, n_ch, W, d_power);
+    return cudaGetLastError();
+}
+
+// ---- ingest -------------------------------------------------------------------------------------------
+// frames[n][n_sensors] (one UDP message per time sample, src/fpga/receiver.h:24-30) ->
+// exposure[n_sensors][n]: serpentine column un-flip + int32 / 2^23 (exact), 32x32 transpose tiles.
+__global__ void __launch_bounds__(256) ingest_kernel(const int32_t *__restrict__ frames, int n, int n_sensors,
+                                                    float *__restrict__ exposure) {
+    __shared__ float tile[32][33];
+    const int s0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        int i = i0 + r, sensor = s0 + tx;
+        if (i < n && sensor < n_sensors) {
+            // every second group of 8 is mirrored (daisy-chained arrays, pipeline.cpp:273-287)
+            int grp = sensor >> 3;
+            int src = (grp & 1) ? sensor : 8 * (1 + grp) - 1 - (sensor & 7);
+            tile[r][tx] = __fdiv_rn((float)frames[(size_t)i * n_sensors + src], 8388608.0f);
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int sensor = s0 + r, i = i0 + tx;
+        if (i < n && sensor < n_sensors) exposure[(size_t)sensor * n + i] = tile[tx][r];
+    }
+}
+
+cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *d_exposure, cudaStream_t st) {
+    dim3 grid((n_sensors + 31) / 32, (n + 31) / 32);
+    ingest_kernel<<<grid, 256, 0, st>>>(d_frames, n, n_sensors, d_exposure);
+    return cudaGetLastError();
+}
+
+}  // namespace bflk

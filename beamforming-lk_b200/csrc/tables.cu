@@ -1,0 +1,156 @@
+// tables.cu -- steering-delay tables on the device.
+//
+// Replaces steering_vector_spherical + the offset/fraction split of the reference
+// (src/geometry/antenna.cpp:89-107,126-134; src/dsp/mimo.cpp:46-54; src/dsp/particle.cpp:37-49).
+// Trigonometry is evaluated on the host in double exactly like rotateZ/rotateY
+// (src/geometry/geometry.cpp:219-233) and arrives here as four floats per direction; the device does
+// only correctly-rounded float mul / fma / sub with every rounding pinned (__f*_rn), so the tables are
+// bit-identical to the host restatement in oracle/oracle.c.
+#include "bflk_internal.h"
+
+namespace bflk {
+
+__device__ __forceinline__ float steer_z(const DirTrig t, float px, float py, float pz) {
+    // rotateZ(float(phi)) * p, k = 0,1,2 from a zero accumulator (documented evaluation order)
+    float xr = __fmaf_rn(0.0f, pz, __fmaf_rn(-t.sz, py, __fmaf_rn(t.cz, px, 0.0f)));
+    float yr = __fmaf_rn(0.0f, pz, __fmaf_rn(t.cz, py, __fmaf_rn(t.sz, px, 0.0f)));
+    float zr = __fmaf_rn(1.0f, pz, __fmaf_rn(0.0f, py, __fmaf_rn(0.0f, px, 0.0f)));
+    // row Z of rotateY(-float(theta)): (-sin, 0, cos)
+    return __fmaf_rn(t.cy, zr, __fmaf_rn(0.0f, yr, __fmaf_rn(-t.sy, xr, 0.0f)));
+}
+
+__global__ void __launch_bounds__(128) steer_tables_kernel(const DirTrig *__restrict__ trig, const float *__restrict__ xyz,
+                                                           int C, float k_scale, int history, int32_t *__restrict__ off,
+                                                           float *__restrict__ frac, int32_t *__restrict__ maxdelay) {
+    extern __shared__ float s_del[];
+    __shared__ float s_red[4];
+    const int d = blockIdx.x;
+    const DirTrig t = trig[d];
+    float mn = INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float z = steer_z(t, xyz[3 * c + 0], xyz[3 * c + 1], xyz[3 * c + 2]);
+        float del = __fmul_rn(z, k_scale);  // compute_delays: row(Z) * float(SAMPLE_RATE / PROPAGATION_SPEED)
+        s_del[c] = del;
+        mn = fminf(mn, del);
+    }
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    mn = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
+    int local_max = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float del = __fsub_rn(s_del[c], mn);  // delays -= minCoeff
+        float ip = truncf(del);               // modf((double)del, &ip): exact for a float argument
+        float fr = __fsub_rn(del, ip);
+        int di = (int)ip;
+        off[(size_t)d * C + c] = history - di;
+        frac[(size_t)d * C + c] = fr;
+        local_max = max(local_max, di);
+    }
+    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((threadIdx.x & 31) == 0 && maxdelay) atomicMax(maxdelay, local_max);
+}
+
+cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d_xyz, int C, float k_scale, int history,
+                                int32_t *d_off, float *d_frac, int32_t *d_maxdelay, cudaStream_t st) {
+    if (n_dir <= 0) return cudaSuccess;
+    steer_tables_kernel<<<n_dir, 128, C * sizeof(float), st>>>(d_trig, d_xyz, C, k_scale, history, d_off, d_frac, d_maxdelay);
+    return cudaGetLastError();
+}
+
+// maxoff / minoff: largest and smallest offset of a caller-supplied LUT (range validation).
+__global__ void max_delay_kernel(const int32_t *__restrict__ off, size_t n, int32_t *maxoff, int32_t *minoff) {
+    int mx = INT_MIN, mo = INT_MAX;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int o = off[i];
+        mx = max(mx, o);
+        mo = min(mo, o);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mo = min(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(maxoff, mx);
+        atomicMin(minoff, mo);
+    }
+}
+
+cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    max_delay_kernel<<<blocks, 256, 0, st>>>(d_off, n, d_maxoff, d_minoff);
+    return cudaGetLastError();
+}
+
+// ---- tile tables ------------------------------------------------------------------------------------
+// Tiles are 2x2 blocks of grid directions (r0..r0+1, c0..c0+1).  A handle's direction range
+// [first, first+count) is a run of the row-major grid; tiles are enumerated over the rows the range
+// touches and directions outside the range get tile_dirs = -1 (computed but not stored).
+__global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
+                                   const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
+                                   int count, TileEntry *__restrict__ tiles, int32_t *__restrict__ tile_dirs,
+                                   int n_tiles, int tile_cols, int row0, int32_t *__restrict__ maxspan) {
+    const int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    const int tr = t / tile_cols, tc = t % tile_cols;
+    int dirs[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int r = row0 + 2 * tr + (q >> 1), c = 2 * tc + (q & 1);
+        int g = (r < rows && c < cols) ? r * cols + c : -1;
+        dirs[q] = g;
+    }
+    // a direction that does not exist (odd grid edge) aliases the tile's first direction
+    int ref = dirs[0];
+    if (threadIdx.x < 4) {
+        int g = dirs[threadIdx.x];
+        int local = (g >= first && g < first + count) ? g - first : -1;
+        tile_dirs[4 * t + threadIdx.x] = local;
+    }
+    int span_max = 0;
+    for (int s = threadIdx.x; s < usable; s += blockDim.x) {
+        const int c = index[s];
+        int o[4];
+        float f[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int g = dirs[q] >= 0 ? dirs[q] : ref;
+            o[q] = off[(size_t)g * C + c];
+            f[q] = frac[(size_t)g * C + c];
+        }
+        int mn = min(min(o[0], o[1]), min(o[2], o[3]));
+        int base = mn & ~1;  // even: the pair-interleaved window is fetched with 16-byte loads
+        TileEntry e;
+        e.base = base;
+        e.row = c;
+        unsigned packed = 0;
+        int span = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int dlt = o[q] - base;
+            span = max(span, dlt);
+            packed |= (unsigned)(dlt & 0xff) << (8 * q);
+            e.frac[q] = f[q];
+        }
+        e.deltas = packed;
+        e.span = span;
+        tiles[(size_t)t * usable + s] = e;
+        span_max = max(span_max, span);
+    }
+    for (int o = 16; o > 0; o >>= 1) span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxspan, span_max);
+}
+
+cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
+                               int rows, int cols, int first, int count, TileEntry *d_tiles, int32_t *d_tile_dirs,
+                               int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
+    const int row0 = (first / cols) & ~1;
+    const int tile_cols = (cols + 1) / 2;
+    build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, d_tiles,
+                                                d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+    return cudaGetLastError();
+}
+
+}  // namespace bflk

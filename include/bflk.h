@@ -1,0 +1,128 @@
+/* bflk.h -- C ABI of the B200-native delay-and-sum path of beamforming-lk.
+ *
+ * This is the whole drop-in boundary: plain C types, caller-owned buffers, no exceptions, no torch
+ * types.  Every entry point returns 0 on success or a negative bflk_status; the message of the last
+ * failure on a handle is available from bflk_last_error().  A handle is "thread-compatible": use it
+ * from one compute thread at a time (the reference calls Worker::update() under Worker::lock,
+ * src/dsp/worker.h:219-222).  There is NO CPU fallback: without a usable CUDA device bflk_create fails.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   bflk_create / bflk_destroy      MIMOWorker / MISOWorker construction + destruction
+ *                                   (src/dsp/mimo.cpp:7-13, src/dsp/miso.cpp:5-13, worker.h:111-114)
+ *   bflk_set_geometry               Antenna::points as built by create_antenna (src/geometry/antenna.cpp:60-87)
+ *   bflk_set_tiled_geometry         create_antenna + place_antenna for n arrays (antenna.cpp:56-87)
+ *   bflk_set_channel_mask           Antenna::index / Antenna::usable written by
+ *                                   AWProcessingUnit::calibrate (aw_processing_unit.cpp:190-200)
+ *   bflk_set_grid_fov               MIMOWorker::computeDelayLUT (src/dsp/mimo.cpp:20-59)
+ *   bflk_set_grid_tables            the same LUT supplied by the caller (offsetDelays / fractionalDelays, mimo.h:86-89)
+ *   bflk_steer_tables               Particle::steer (src/dsp/particle.cpp:37-49)
+ *   bflk_power_map*                 MIMOWorker::update (src/dsp/mimo.cpp:97-151) -> powerdB
+ *   bflk_miso*                      Particle::steer + Particle::das + Particle::beam
+ *                                   (src/dsp/particle.cpp:37-103) as used by MISOWorker::update (miso.cpp:39-46)
+ *   bflk_heatmap                    MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95)
+ *   bflk_calibrate                  AWProcessingUnit::calibrate mask (aw_processing_unit.cpp:126-200)
+ *   bflk_ingest_i32                 Pipeline::receive_exposure conversion (src/fpga/pipeline.cpp:260-297)
+ */
+#ifndef BFLK_H
+#define BFLK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFLK_VERSION 1
+
+typedef enum bflk_status {
+    BFLK_OK = 0,
+    BFLK_ERR_INVALID = -1,   /* bad argument / inconsistent configuration */
+    BFLK_ERR_STATE = -2,     /* call sequence: geometry / grid not set yet */
+    BFLK_ERR_CUDA = -3,      /* CUDA runtime failure (message has the CUDA error string) */
+    BFLK_ERR_NO_DEVICE = -4, /* no usable sm_100 device: there is no CPU fallback */
+    BFLK_ERR_RANGE = -5      /* a delay does not fit the history / window the caller configured */
+} bflk_status;
+
+/* Runtime replacement for the reference's compile-time constants. Zero-initialise, then fill;
+ * bflk_default_config() gives the reference's values. */
+typedef struct bflk_config {
+    int32_t n_channels;       /* C: physical microphones (n_arrays * 64; ELEMENTS, antenna.h:20) */
+    int32_t frame_len;        /* N: samples per frame (N_SAMPLES 256, streams.hpp:28) */
+    int32_t history;          /* H: offset = H - int(delay) (N_SAMPLES in mimo.cpp:50 / particle.cpp:44) */
+    int32_t window_len;       /* W: floats per channel handed to single-frame calls (N_ITEMS_BUFFER 1024) */
+    double sample_rate;       /* SAMPLE_RATE 48828.0, antenna.h:17 */
+    double propagation_speed; /* PROPAGATION_SPEED 340.0, antenna.h:16 */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved;
+} bflk_config;
+
+typedef struct bflk_handle bflk_handle;
+
+void bflk_default_config(bflk_config *cfg);
+int bflk_version(void);
+
+int bflk_create(const bflk_config *cfg, bflk_handle **out);
+int bflk_destroy(bflk_handle *h);
+/* Message of the last failure on h (h == NULL: last failure of bflk_create on this thread). */
+const char *bflk_last_error(const bflk_handle *h);
+
+/* ---- geometry, mask, steering tables ------------------------------------------------------------ */
+/* xyz[C][3] in metres (row c = element c; same memory as the reference's column-major 3 x C matrix). */
+int bflk_set_geometry(bflk_handle *h, const float *xyz, int32_t n_channels);
+/* n_tiles 8x8 arrays at 2 cm pitch (create_antenna), tile a translated by origins[a][3]; C = 64*n_tiles. */
+int bflk_set_tiled_geometry(bflk_handle *h, int32_t n_tiles, const float *origins);
+int bflk_get_geometry(const bflk_handle *h, float *xyz);
+/* index[usable]: physical channels summed, IN THIS ORDER (mimo.cpp:124-130). NULL = all channels. */
+int bflk_set_channel_mask(bflk_handle *h, const int32_t *index, int32_t usable);
+
+/* rows x cols direction grid over fov degrees; direction k = r*cols + c. Builds the LUT on the device. */
+int bflk_set_grid_fov(bflk_handle *h, int32_t rows, int32_t cols, float fov_deg);
+/* Caller-supplied LUT [D][C] (physical element index), offsets as in the reference (H - int(delay)). */
+int bflk_set_grid_tables(bflk_handle *h, const int32_t *offsets, const float *fractions, int32_t n_directions);
+/* Multi-GPU sharding: this handle computes directions [first, first+count) of the grid only. */
+int bflk_set_direction_range(bflk_handle *h, int32_t first, int32_t count);
+int bflk_get_n_directions(const bflk_handle *h, int32_t *total, int32_t *first, int32_t *count);
+int bflk_get_grid(const bflk_handle *h, double *theta, double *phi);            /* [D] each */
+int bflk_get_tables(const bflk_handle *h, int32_t *offsets, float *fractions);  /* [D][C] */
+/* Particle::steer for T directions: offsets / fractions [T][C], computed by the device table kernel. */
+int bflk_steer_tables(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets,
+                      int32_t *offsets, float *fractions);
+
+/* ---- full-grid power map (MIMO) ------------------------------------------------------------------- */
+/* window[C][W] channel-major snapshot exactly as read_stream() produces it (oldest sample first);
+ * power_out[count] for this handle's direction range.  Host buffers; H2D + kernel + D2H, synchronous. */
+int bflk_power_map(bflk_handle *h, const float *window, float *power_out);
+/* Batched: stream[C][T] channel-major continuous samples; frame b uses window stream[c][b*N .. b*N+W'),
+ * i.e. consecutive frames advance by N samples like Streams::forward().  T >= (B-1)*N + H + N + 1.
+ * power_out[B][count]. */
+int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
+int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                             float *power_dev, void *cuda_stream);
+/* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel. */
+int bflk_set_kernel(bflk_handle *h, int32_t which);
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t bflk_launch_count(const bflk_handle *h);
+
+/* ---- dynamic steering (MISO) --------------------------------------------------------------------- */
+/* For each target t: steer(theta[t], phi[t]); audio_out[t][N] = Particle::das; power_out[t] = Particle::beam.
+ * Either output may be NULL. window[C][W] as in bflk_power_map. */
+int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window,
+              float *audio_out, float *power_out);
+int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets,
+                  const float *window_dev, float *audio_dev, float *power_dev, void *cuda_stream);
+
+/* ---- neighbours of the path ------------------------------------------------------------------------ */
+/* populateHeatmap: heat[count] = uchar(clip(255 * p / max)), argmax / max of the map. */
+int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv);
+/* calibrate(): signals[64][W] of one array -> index[<=64], correction[<=64]; *usable = count. */
+int bflk_calibrate(bflk_handle *h, const float *signals, int32_t window_len, float reference_power_level,
+                   int32_t *index, float *correction, int32_t *usable, float *median, float *mean);
+/* receive_exposure(): wire frames[n][n_sensors] int32 -> exposure[n_sensors][n] float (un-flip, / 2^23). */
+int bflk_ingest_i32(bflk_handle *h, const int32_t *frames, int32_t n, int32_t n_sensors, float *exposure);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFLK_H */

@@ -1,0 +1,239 @@
+/* oracle.c -- see oracle.h.  TEST INFRASTRUCTURE ONLY, never linked into the product.
+ * Build with -O2 -ffp-contract=off -fno-fast-math so every float operation below rounds exactly
+ * where it is written; explicit fmaf() marks the reference's fused operations. */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- a1 ----------------------------------------------------------------------------------- */
+void orc_create_antenna(float *xyz, int columns, int rows, float distance) {
+    /* src/geometry/antenna.cpp:60-76.  Note the reference mixes rows/columns in the centring
+     * terms (x uses rows, y uses columns); kept as written. */
+    float half = distance / 2;
+    int i = 0;
+    for (int r = 0; r < rows; r++) {
+        for (int c = 0; c < columns; c++) {
+            xyz[3 * i + 0] = (float)c * distance - (float)rows * half + half;
+            xyz[3 * i + 1] = (float)r * distance - (float)columns * half + half;
+            xyz[3 * i + 2] = 0.f;
+            i++;
+        }
+    }
+}
+
+void orc_create_tiled_antenna(float *xyz, int n_tiles, const float *origins) {
+    float tile[3 * ORC_ELEMENTS];
+    orc_create_antenna(tile, ORC_COLUMNS, ORC_ROWS, ORC_DISTANCE);
+    for (int a = 0; a < n_tiles; a++)
+        for (int e = 0; e < ORC_ELEMENTS; e++)
+            for (int k = 0; k < 3; k++)
+                xyz[3 * (a * ORC_ELEMENTS + e) + k] = tile[3 * e + k] + origins[3 * a + k];
+}
+
+/* ---- a2-a5 -------------------------------------------------------------------------------- */
+void orc_steering_vector_spherical(const float *xyz, int C, double theta, double phi, float *delays) {
+    /* steer(): rotateY(-float(theta)) * (rotateZ(float(phi)) * points), antenna.cpp:99-107.
+     * Matrix entries: float(cos/sin((double)angle)), geometry.cpp:219-233.
+     * Product evaluation order (Eigen 3.4 GEMM path, FMA-contracted, k = 0,1,2 from a zero
+     * accumulator) is FIXED here as acc = fma(R[i][k], p[k], acc). */
+    const float az = (float)phi;
+    const float ay = -(float)theta;
+    const float cz = (float)cos((double)az), sz = (float)sin((double)az);
+    const float cy = (float)cos((double)ay), sy = (float)sin((double)ay);
+    const float Rz[3][3] = {{cz, -sz, 0.0f}, {sz, cz, 0.0f}, {0.0f, 0.0f, 1.0f}};
+    const float Ry[3][3] = {{cy, 0.0f, sy}, {0.0f, 1.0f, 0.0f}, {-sy, 0.0f, cy}};
+    /* compute_delays(): row(Z) * (SAMPLE_RATE / PROPAGATION_SPEED) as float x float, then
+     * subtract the minimum, antenna.cpp:89-97. */
+    const float k = (float)(ORC_SAMPLE_RATE / ORC_PROPAGATION_SPEED);
+    float mn = INFINITY;
+    for (int c = 0; c < C; c++) {
+        const float *p = &xyz[3 * c];
+        float q[3];
+        for (int i = 0; i < 3; i++) {
+            float acc = 0.0f;
+            for (int j = 0; j < 3; j++) acc = fmaf(Rz[i][j], p[j], acc);
+            q[i] = acc;
+        }
+        float acc = 0.0f;
+        for (int j = 0; j < 3; j++) acc = fmaf(Ry[2][j], q[j], acc);
+        float d = acc * k;
+        delays[c] = d;
+        if (d < mn) mn = d;
+    }
+    for (int c = 0; c < C; c++) delays[c] = delays[c] - mn;
+}
+
+void orc_split_delays(const float *delays, int C, int history, int32_t *offsets, float *fractions) {
+    for (int c = 0; c < C; c++) {
+        double ip;
+        float fraction = (float)modf((double)delays[c], &ip);
+        offsets[c] = history - (int)ip;
+        fractions[c] = fraction;
+    }
+}
+
+/* ---- a6 ----------------------------------------------------------------------------------- */
+void orc_mimo_grid(int rows, int cols, double fov_deg, double *theta, double *phi) {
+    /* src/dsp/mimo.cpp:20-43; TO_RADIANS(a) = a * M_PI / 180.0 (geometry.h). */
+    double fovRadian = fov_deg * (M_PI / 180.0);
+    double separationRows = sin(fovRadian / 2.0) / ((double)rows / 2.0);
+    double separationColumns = sin(fovRadian / 2.0) / ((double)cols / 2.0);
+    int k = 0;
+    for (int r = 0; r < rows; r++) {
+        for (int c = 0; c < cols; c++) {
+            double y = (double)r * separationRows - (double)rows * separationRows / 2.0 + separationRows / 2.0;
+            double x = (double)c * separationColumns - (double)cols * separationColumns / 2.0 + separationColumns / 2.0;
+            double norm = sqrt(pow(x, 2) + pow(y, 2));
+            if (norm == 0.0) { theta[k] = 0.0; phi[k] = 0.0; k++; continue; }
+            x /= norm;
+            y /= norm;
+            if (norm > 1.0) norm = 1.0;
+            theta[k] = asin(norm);
+            phi[k] = atan2(y, x);
+            k++;
+        }
+    }
+}
+
+void orc_mimo_lut(const float *xyz, int C, int rows, int cols, double fov_deg, int history,
+                  int32_t *offsets, float *fractions) {
+    int D = rows * cols;
+    double *theta = (double *)malloc(sizeof(double) * D), *phi = (double *)malloc(sizeof(double) * D);
+    float *del = (float *)malloc(sizeof(float) * C);
+    orc_mimo_grid(rows, cols, fov_deg, theta, phi);
+    for (int k = 0; k < D; k++) {
+        orc_steering_vector_spherical(xyz, C, theta[k], phi[k], del);
+        orc_split_delays(del, C, history, &offsets[(size_t)k * C], &fractions[(size_t)k * C]);
+    }
+    free(theta); free(phi); free(del);
+}
+
+/* ---- a9 ----------------------------------------------------------------------------------- */
+void orc_delay(float *out, const float *signal, float fraction, int n) {
+    for (int i = 0; i < n; i++)
+        out[i] = out[i] + fmaf(fraction, signal[i] - signal[i + 1], signal[i + 1]);
+}
+
+/* ---- a10 ---------------------------------------------------------------------------------- */
+static float hp_power(const float *out, int n) {
+    /* src/dsp/mimo.cpp:131-135 / particle.cpp:68-72; powf(MA, 2) == MA * MA; summed in index order. */
+    float power = 0.0f;
+    for (int i = 1; i < n - 1; i++) {
+        float MA = out[i] * 0.5f - 0.25f * (out[i + 1] + out[i - 1]);
+        power += MA * MA;
+    }
+    return power;
+}
+
+static void das_one(const float *window, int W, int n, const int *index, int usable,
+                    const int32_t *offsets, const float *fractions, float *out) {
+    memset(out, 0, sizeof(float) * n);
+    for (int s = 0; s < usable; s++) {
+        int i = index[s];
+        orc_delay(out, &window[(size_t)i * W + offsets[i]], fractions[i], n);
+    }
+}
+
+void orc_mimo_das(const float *window, int C, int W, int n, const int *index, int usable,
+                  const int32_t *offsets, const float *fractions, int D, float *out) {
+    for (int m = 0; m < D; m++)
+        das_one(window, W, n, index, usable, &offsets[(size_t)m * C], &fractions[(size_t)m * C], &out[(size_t)m * n]);
+}
+
+void orc_mimo_update(const float *window, int C, int W, int n, const int *index, int usable,
+                     const int32_t *offsets, const float *fractions, int D, float *power) {
+    float *out = (float *)malloc(sizeof(float) * n);
+    for (int m = 0; m < D; m++) {
+        das_one(window, W, n, index, usable, &offsets[(size_t)m * C], &fractions[(size_t)m * C], out);
+        float p = hp_power(out, n);
+        p /= (float)(n * usable);   /* mimo.cpp:137, count == usable */
+        power[m] = p;
+    }
+    free(out);
+}
+
+/* ---- a11 / a12 ---------------------------------------------------------------------------- */
+double orc_particle_beam(const float *window, int W, int n, const int *index, int usable,
+                         const int32_t *offsets, const float *fractions, float *out_scratch) {
+    das_one(window, W, n, index, usable, offsets, fractions, out_scratch);
+    float p = hp_power(out_scratch, n);
+    p /= (float)n;                  /* particle.cpp:79 */
+    return (double)p;
+}
+
+void orc_particle_das(const float *window, int W, int n, const int *index, int usable,
+                      const int32_t *offsets, const float *fractions, float *out) {
+    das_one(window, W, n, index, usable, offsets, fractions, out);
+}
+
+/* ---- a13 ---------------------------------------------------------------------------------- */
+int orc_populate_heatmap(const float *power, int D, uint8_t *heat, float *max_out) {
+    float maxV = 0.0f;
+    int arg = 0;
+    for (int i = 0; i < D; i++)
+        if (power[i] > maxV) { maxV = power[i]; arg = i; }
+    for (int i = 0; i < D; i++) {
+        double db = pow((double)(power[i] / maxV), 1);   /* mimo.cpp:86: float division, widened */
+        db *= 255.0;
+        if (db < 0.0) db = 0.0;
+        if (db > 255.0) db = 255.0;
+        heat[i] = (uint8_t)db;
+    }
+    if (max_out) *max_out = maxV;
+    return arg;
+}
+
+/* ---- a15 ---------------------------------------------------------------------------------- */
+static int cmp_float(const void *a, const void *b) {
+    float x = *(const float *)a, y = *(const float *)b;
+    return (x > y) - (x < y);
+}
+
+int orc_calibrate(const float *signals, int W, float reference_power_level, int *index,
+                  float *correction, float *median_out, float *mean_out) {
+    /* src/aw_processing_unit/aw_processing_unit.cpp:126-200 */
+    float power[ORC_ELEMENTS], medians[ORC_ELEMENTS];
+    float mean = 0.0f;
+    for (int s = 0; s < ORC_ELEMENTS; s++) {
+        float pv = 0.0f;
+        for (int i = 0; i < W; i++) pv += signals[(size_t)s * W + i] * signals[(size_t)s * W + i];
+        pv /= (float)W;
+        mean += pv;
+        power[s] = pv;
+    }
+    memcpy(medians, power, sizeof(power));
+    qsort(medians, ORC_ELEMENTS, sizeof(float), cmp_float);
+    float median = (float)((medians[ORC_ELEMENTS / 2] + medians[ORC_ELEMENTS / 2 + 1]) / 2.0);
+    int count = 0;
+    for (int s = 0; s < ORC_ELEMENTS; s++) {
+        float diff = fabsf(power[s] - median);
+        if (diff > 1e-4) {
+        } else if (power[s] < median * 1e-3) {
+        } else {
+            index[count] = s;
+            count++;
+            mean += power[s];
+        }
+    }
+    mean /= (float)count;
+    for (int s = 0; s < count; s++) correction[s] = reference_power_level / power[index[s]];
+    if (median_out) *median_out = median;
+    if (mean_out) *mean_out = mean;
+    return count;
+}
+
+/* ---- f1 ----------------------------------------------------------------------------------- */
+void orc_ingest(const int32_t *frames, int n, int n_sensors, float *exposure) {
+    /* src/fpga/pipeline.cpp:260-297 */
+    for (int i = 0; i < n; i++) {
+        int inverted = 0;
+        for (unsigned sensor_index = 0; sensor_index < (unsigned)n_sensors; sensor_index++) {
+            unsigned index;
+            if (sensor_index % ORC_COLUMNS == 0) inverted = !inverted;
+            if (inverted) index = ORC_COLUMNS * (1 + sensor_index / ORC_COLUMNS) - 1 - sensor_index % ORC_COLUMNS;
+            else index = sensor_index;
+            exposure[(size_t)sensor_index * n + i] = (float)frames[(size_t)i * n_sensors + index] / 8388608.0f;
+        }
+    }
+}

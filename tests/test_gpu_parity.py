@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden vectors.  Bars (BASELINE.json north_star): steering tables bit-exact; delayed sums bit-exact;
+power maps <= 1e-4 max relative error with identical peak direction."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+POWER_RTOL = 1e-4   # north_star tolerance for floating-point power maps
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a.astype(np.float64) - b) / np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def bf():
+    import bflk
+    return bflk
+
+
+def make(bf, c, **kw):
+    return bf.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"],
+                         frame_len=c["N"], history=c["H"], window_len=c["W"], **kw)
+
+
+# ---- steering tables: bit-exact ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.CONFIGS))
+def test_tables_bit_exact(bf, oracle, golden, name):
+    c = cases.CONFIGS[name]
+    w = make(bf, c)
+    off, fr = w.tables()
+    g = golden["tables"]
+    assert np.array_equal(sha(off), g[f"{name}_off_sha"])
+    assert np.array_equal(sha(fr), g[f"{name}_frac_sha"])
+    xyz = oracle.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    assert np.array_equal(w.geometry(), xyz)
+    ooff, ofr = oracle.mimo_lut(xyz, c["rows"], c["cols"], c["fov"], c["H"])
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(fr.view(np.uint32), ofr.view(np.uint32))
+    th, ph = w.grid()
+    oth, oph = oracle.mimo_grid(c["rows"], c["cols"], c["fov"])
+    assert np.array_equal(th, oth) and np.array_equal(ph, oph)
+
+
+def test_odd_grid_tables(bf, golden):
+    w = bf.MIMOWorker(cases.origins(1, 1), 9, 9, 120.0)
+    off, fr = w.tables()
+    assert np.array_equal(off, golden["tables"]["odd9_off"])
+    assert np.array_equal(fr.view(np.uint32), golden["tables"]["odd9_frac"].view(np.uint32))
+
+
+def test_dynamic_steer_tables_bit_exact(bf, oracle, golden):
+    th, ph = cases.cfg4_targets()
+    w = bf.MISOWorker(cases.origins(4, 2))
+    off, fr = w.steer_tables(th, ph)
+    assert np.array_equal(off, golden["tables"]["cfg4_off"])
+    assert np.array_equal(fr.view(np.uint32), golden["tables"]["cfg4_frac"].view(np.uint32))
+    rng = np.random.default_rng(7)
+    th, ph = rng.random(257) * np.pi / 2, rng.random(257) * 2 * np.pi
+    off, fr = w.steer_tables(th, ph)
+    ooff, ofr = oracle.steer_tables(oracle.create_tiled_antenna(cases.origins(4, 2)), th, ph)
+    assert np.array_equal(off, ooff) and np.array_equal(fr.view(np.uint32), ofr.view(np.uint32))
+
+
+# ---- the golden snapshot through every entry point ----------------------------------------------------------
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_snapshot_power_map(bf, golden, kernel):
+    g = golden["snapshot"]
+    w = bf.MIMOWorker(cases.origins(1, 1), 16, 16, 180.0)
+    w.set_kernel(kernel)
+    p = w.update(g["window"])
+    assert rel_err(p, g["power"]) <= POWER_RTOL
+    assert rel_err(p, g["ref_power"]) <= POWER_RTOL         # compiled reference delay() + fast-math sum
+    assert int(np.argmax(p)) == int(np.argmax(g["power"])) == int(np.argmax(g["ref_power"]))
+    w.set_channel_mask(g["mask"])
+    pm = w.update(g["window"])
+    assert rel_err(pm, g["power_masked"]) <= POWER_RTOL
+    heat, arg, mx = w.populateHeatmap()
+    assert arg == int(np.argmax(pm)) and heat.max() == 255
+
+
+def test_snapshot_miso_bit_exact_audio(bf, golden):
+    g = golden["snapshot"]
+    w = bf.MISOWorker(cases.origins(1, 1))
+    w.steer(g["miso_theta"], g["miso_phi"])
+    audio, power = w.update(g["window"])
+    assert np.array_equal(audio.view(np.uint32), g["miso_audio"].view(np.uint32))   # das(): bit-exact
+    assert rel_err(power, g["miso_beam"]) <= POWER_RTOL                             # beam()
+    a2, none = w.miso(g["miso_theta"], g["miso_phi"], g["window"], want_power=False)
+    assert none is None and np.array_equal(a2, audio)
+
+
+def test_snapshot_heatmap_calibrate_ingest(bf, golden):
+    g = golden["snapshot"]
+    b = bf.Beamformer()
+    heat, arg, mx = b.heatmap(g["power"])
+    assert np.array_equal(heat, g["heat"]) and arg == int(g["heat_argmax"]) and mx == float(g["heat_max"])
+    cal = g["window"].copy()
+    cal[5] *= 0.0
+    cal[9] *= 3.0
+    cal[33] *= 0.5
+    idx, corr, med, mean = b.calibrate(cal)
+    assert np.array_equal(idx, g["cal_index"]) and np.array_equal(corr, g["cal_corr"])
+    assert med == float(g["cal_median"]) and mean == float(g["cal_mean"])
+    assert np.array_equal(b.ingest_i32(g["wire"]), g["exposure"])
+
+
+# ---- configurations of BASELINE.json against the oracle on the same seeded input ------------------------------
+def _synth_window(bf, c, n_samples=None, sigma=1e-3):
+    from bflk import synth
+    xyz = synth.tile_geometry(cases.origins(c["nx"], c["ny"]))
+    return synth.make_stream(xyz, n_samples or c["W"], sigma=sigma)
+
+
+@pytest.mark.parametrize("name,kernel", [("cfg1", 0), ("cfg2", 0), ("cfg3", 0), ("cfg3", 1)])
+def test_config_power_map_vs_oracle(bf, oracle, name, kernel):
+    c = cases.CONFIGS[name]
+    w = make(bf, c)
+    w.set_kernel(kernel)
+    window = _synth_window(bf, c)
+    p = w.update(window)
+    off, fr = w.tables()
+    po = oracle.mimo_update(window, off, fr, n=c["N"])
+    assert rel_err(p, po) <= POWER_RTOL
+    assert int(np.argmax(p)) == int(np.argmax(po))
+    # physics: the 9 kHz boresight tone dominates after the high-pass -> peak next to the grid centre
+    r, cc = divmod(int(np.argmax(p)), c["cols"])
+    assert abs(r - (c["rows"] - 1) / 2) <= 1.5 and abs(cc - (c["cols"] - 1) / 2) <= 1.5
+
+
+def test_noise_free_deep_nulls(bf, oracle):
+    """Side-lobe nulls 10 orders below the peak: only a sequential channel sum stays within 1e-4."""
+    c = cases.CONFIGS["cfg3"]
+    from bflk import synth
+    xyz = synth.tile_geometry(cases.origins(c["nx"], c["ny"]))
+    window = synth.make_stream(xyz, c["W"], sources=((np.deg2rad(20.0), np.deg2rad(30.0), 3000.0, 1e-2),), sigma=0.0)
+    w = make(bf, c)
+    p = w.update(window)
+    off, fr = w.tables()
+    po = oracle.mimo_update(window, off, fr)
+    assert rel_err(p, po) <= POWER_RTOL
+    assert int(np.argmax(p)) == int(np.argmax(po))
+
+
+def test_cfg5_subset_and_properties(bf, oracle):
+    """256x256 x 4096-sample x 512-channel stress shape: oracle on a direction subset + size-independent
+    properties on the full grid."""
+    c = cases.CONFIGS["cfg5"]
+    w = make(bf, c)
+    window = _synth_window(bf, c)
+    D = c["rows"] * c["cols"]
+    p = w.update(window)
+    assert p.shape == (D,) and np.all(np.isfinite(p)) and p.min() > 0
+    off, fr = w.tables()
+    sel = np.r_[0:4, 128 * 256 + 126:128 * 256 + 130, D - 3:D, np.arange(17, D, 4099)]
+    po = oracle.mimo_update(window, off[sel], fr[sel], n=c["N"])
+    assert rel_err(p[sel], po) <= POWER_RTOL
+    # exact scaling: inputs x 2 (a power of two) -> every power x 4, bit for bit
+    p2 = w.update(window * np.float32(2.0))
+    assert np.array_equal(p2, p * np.float32(4.0))
+    # direction sharding: the concatenation of shard maps equals the full map, bit for bit
+    parts = []
+    for g in range(4):
+        w.set_direction_range(g * D // 4, D // 4)
+        parts.append(w.update(window))
+    assert np.array_equal(np.concatenate(parts), p)
+    # peak at the grid centre (9 kHz boresight tone)
+    r, cc = divmod(int(np.argmax(p)), 256)
+    assert abs(r - 127.5) <= 1.5 and abs(cc - 127.5) <= 1.5
+
+
+def test_cfg4_miso_vs_oracle(bf, oracle):
+    th, ph = cases.cfg4_targets()
+    c = cases.CFG4
+    w = bf.MISOWorker(cases.origins(c["nx"], c["ny"]))
+    window = _synth_window(bf, c)
+    w.steer(th, ph)
+    audio, power = w.update(window)
+    xyz = oracle.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    off, fr = oracle.steer_tables(xyz, th, ph)
+    for t in range(c["T"]):
+        assert np.array_equal(audio[t].view(np.uint32), oracle.particle_das(window, off[t], fr[t]).view(np.uint32))
+        assert abs(power[t] - oracle.particle_beam(window, off[t], fr[t])) <= POWER_RTOL * power[t]
+
+
+# ---- batching, sharding, masks, edge cases -----------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_batch_equals_single_frames(bf, oracle, kernel):
+    c = cases.CONFIGS["cfg3"]
+    B = 5
+    w = make(bf, c)
+    w.set_kernel(kernel)
+    stream = _synth_window(bf, c, n_samples=(B - 1) * c["N"] + c["W"])
+    pb = w.power_map_batch(stream, B)
+    assert pb.shape == (B, 1024)
+    for b in range(B):
+        single = w.update(np.ascontiguousarray(stream[:, b * c["N"]: b * c["N"] + c["W"]]))
+        assert np.array_equal(pb[b], single)
+    off, fr = w.tables()
+    po = oracle.mimo_update(np.ascontiguousarray(stream[:, 3 * 256: 3 * 256 + 1024]), off, fr)
+    assert rel_err(pb[3], po) <= POWER_RTOL
+
+
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
+    c = cases.CONFIGS["cfg2"]
+    w = make(bf, c)
+    w.set_kernel(kernel)
+    window = _synth_window(bf, c)
+    off, fr = w.tables()
+    full = w.update(window)
+    for first, count in [(0, 1), (63, 2), (65, 131), (4095, 1), (1000, 3096), (0, 4096)]:
+        w.set_direction_range(first, count)
+        assert np.array_equal(w.update(window), full[first:first + count])
+    w.set_direction_range(0, 4096)
+    rng = np.random.default_rng(3)
+    mask = np.sort(rng.choice(256, 201, replace=False)).astype(np.int32)
+    w.set_channel_mask(mask)
+    pm = w.update(window)
+    po = oracle.mimo_update(window, off, fr, index=mask)
+    assert rel_err(pm, po) <= POWER_RTOL
+    w.set_channel_mask(np.array([17], np.int32))           # a single microphone
+    p1 = w.update(window)
+    assert rel_err(p1, oracle.mimo_update(window, off, fr, index=np.array([17], np.int32))) <= POWER_RTOL
+
+
+def test_caller_supplied_tables_and_errors(bf, oracle):
+    import bflk
+    xyz = oracle.create_antenna()
+    off, fr = oracle.mimo_lut(xyz, 6, 10, 100.0)
+    b = bflk.Beamformer()
+    with pytest.raises(bflk.BflkError) as e:
+        b.power_map(np.zeros((64, 1024), np.float32))
+    assert e.value.code == -2                                   # BFLK_ERR_STATE
+    b.set_geometry(xyz)
+    b.set_grid_tables(off, fr)
+    from bflk import synth
+    window = synth.make_stream(xyz, 1024)
+    assert rel_err(b.power_map(window), oracle.mimo_update(window, off, fr)) <= POWER_RTOL
+    bad = off.copy()
+    bad[3, 5] = -1
+    with pytest.raises(bflk.BflkError) as e:
+        b.set_grid_tables(bad, fr)
+    assert e.value.code == -5                                   # BFLK_ERR_RANGE
+    with pytest.raises(bflk.BflkError):
+        b.set_direction_range(0, 61)                            # grid was invalidated by the failed call
+    # a geometry whose delays exceed the history is refused, not silently wrapped
+    far = bflk.Beamformer(n_channels=128)
+    with pytest.raises(bflk.BflkError) as e:
+        far.set_tiled_geometry(np.array([[-1.0, 0, 0], [1.0, 0, 0]], np.float32))
+        far.set_grid_fov(8, 8, 180.0)
+    assert e.value.code == -5
+
+
+def test_launch_counter(bf, golden):
+    w = bf.MIMOWorker(cases.origins(1, 1), 16, 16, 180.0)
+    n0 = w.launch_count()
+    w.update(golden["snapshot"]["window"])
+    assert w.launch_count() > n0

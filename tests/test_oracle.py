@@ -1,0 +1,172 @@
+"""CPU tests of the oracle: against the committed golden vectors and against the compiled,
+unmodified reference kernel (oracle/_ref, built from /root/reference/src/dsp/delay.cpp + streams.hpp)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import cases
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def test_create_antenna_matches_reference_formula(oracle, golden):
+    xyz = oracle.create_antenna()
+    assert np.array_equal(xyz, golden["tables"]["antenna_xyz"])
+    # src/geometry/antenna.cpp:68-76: element 0 at (-0.07, -0.07), pitch 0.02, row-major i = r*8 + c
+    assert np.allclose(xyz[0], [-0.07, -0.07, 0.0], atol=1e-7)
+    assert np.allclose(xyz[9] - xyz[0], [0.02, 0.02, 0.0], atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(cases.CONFIGS))
+def test_tables_match_golden(oracle, golden, name):
+    c = cases.CONFIGS[name]
+    g = golden["tables"]
+    xyz = oracle.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    off, fr = oracle.mimo_lut(xyz, c["rows"], c["cols"], c["fov"], c["H"])
+    assert np.array_equal(sha(off), g[f"{name}_off_sha"])
+    assert np.array_equal(sha(fr), g[f"{name}_frac_sha"])
+    rows = g[f"{name}_rows"]
+    assert np.array_equal(off[rows], g[f"{name}_off_rows"])
+    assert np.array_equal(fr[rows].view(np.uint32), g[f"{name}_frac_rows"].view(np.uint32))
+    # contract of the split (mimo.cpp:46-54): 0 <= fraction < 1, offset = H - int(delay) in [0, H]
+    assert fr.min() >= 0.0 and fr.max() < 1.0
+    assert off.max() <= c["H"] and off.min() == c["H"] - int(g[f"{name}_max_delay"]) >= 0
+    # the closest element of every direction has zero delay (antenna.cpp:94)
+    assert np.all((off == c["H"]).any(axis=1))
+
+
+def test_odd_grid_degenerate_centre(oracle, golden):
+    xyz = oracle.create_antenna()
+    off, fr = oracle.mimo_lut(xyz, 9, 9, 120.0)
+    assert np.array_equal(off, golden["tables"]["odd9_off"])
+    assert np.array_equal(fr, golden["tables"]["odd9_frac"])
+    th, ph = oracle.mimo_grid(9, 9, 120.0)
+    # centre cell: x, y cancel to ~1e-17 (or exactly 0 -> defined as boresight), never NaN
+    assert np.all(np.isfinite(th)) and np.all(np.isfinite(ph)) and th[40] < 1e-12
+    assert np.all(off[40] == 256) and np.all(fr[40] < 1e-6)
+    th3, ph3 = oracle.mimo_grid(1, 1, 90.0)          # exact 0/0 case
+    assert th3[0] == 0.0 and ph3[0] == 0.0
+
+
+def test_delay_kernel_semantics(oracle):
+    # src/dsp/delay.cpp:16-26 probe from SURVEY.md 8c: ramp input, fraction 0.25
+    sig = np.arange(512, dtype=np.float32)
+    out = np.zeros(256, np.float32)
+    oracle.delay(out, sig[253:].copy(), 0.25)
+    assert out[0] == np.float32(253.75) and out[255] == np.float32(508.75)
+    oracle.delay(out, sig[253:].copy(), 0.25)           # accumulates
+    assert out[0] == np.float32(507.5)
+
+
+def test_delay_bit_exact_vs_compiled_reference(oracle):
+    R = oracle.ref()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    assert R.ref_n_samples() == 256
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        sig = (rng.standard_normal(257) * 10.0 ** rng.integers(-6, 3)).astype(np.float32)
+        acc = rng.standard_normal(256).astype(np.float32)
+        f = np.float32(rng.random())
+        a, b = acc.copy(), acc.copy()
+        oracle.delay(a, sig, f)
+        R.ref_delay(b, sig, f)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_window_semantics_vs_reference_streams(oracle):
+    """a8: after forward(), position -> oldest block; get_signal(i, off) = ring[position/4 + off]."""
+    R = oracle.ref()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    frames = np.arange(6 * 256, dtype=np.float32)
+    window = np.zeros(1024, np.float32)
+    probe = np.zeros(257, np.float32)
+    assert R.ref_streams_window(frames, 6, window, 253, probe) == 1024
+    # six frames written: the ring holds frames 2..5, oldest first
+    assert np.array_equal(window, frames[512:1536])
+    assert window[0] == 512 and window[768] == 1280
+    assert np.array_equal(probe, window[253:253 + 257])
+    out = np.zeros(256, np.float32)
+    oracle.delay(out, probe, 0.25)
+    assert out[0] == np.float32(765.75)
+
+
+def test_snapshot_matches_golden_and_reference(oracle, golden):
+    g = golden["snapshot"]
+    window = g["window"]
+    xyz = oracle.create_antenna()
+    off, fr = oracle.mimo_lut(xyz, 16, 16, 180.0)
+    power = oracle.mimo_update(window, off, fr)
+    das = oracle.mimo_das(window, off, fr)
+    assert np.array_equal(power, g["power"])
+    assert np.array_equal(das[g["das_sel"]], g["das"])
+    # compiled reference delay(): delayed sums bit-identical, power within fast-math reassociation
+    assert np.max(np.abs(g["ref_power"] - power) / power) < 1e-5
+    assert int(np.argmax(power)) == int(np.argmax(g["ref_power"]))
+    if oracle.ref() is not None:
+        rp, rd = oracle.ref_mimo_update(window, off, fr, want_das=True)
+        assert np.array_equal(rd, das)
+        assert np.array_equal(rp, g["ref_power"])
+        rp4 = oracle.ref_mimo_update(window, off, fr, n_threads=4)
+        assert np.array_equal(rp4, rp)
+    assert np.array_equal(oracle.mimo_update(window, off, fr, index=g["mask"]), g["power_masked"])
+    # the reference's own synthetic tone (9 kHz from boresight, pipeline.cpp:115) wins after the high-pass
+    assert int(np.argmax(power)) in (119, 120, 135, 136)
+
+
+def test_particle_matches_golden(oracle, golden):
+    g = golden["snapshot"]
+    xyz = oracle.create_antenna()
+    soff, sfr = oracle.steer_tables(xyz, g["miso_theta"], g["miso_phi"])
+    assert np.array_equal(soff, g["miso_off"]) and np.array_equal(sfr, g["miso_frac"])
+    for t in range(4):
+        assert np.array_equal(oracle.particle_das(g["window"], soff[t], sfr[t]), g["miso_audio"][t])
+        assert oracle.particle_beam(g["window"], soff[t], sfr[t]) == g["miso_beam"][t]
+    # beam() normalises by N only, update() by N*count (particle.cpp:79 vs mimo.cpp:137)
+    off, fr = oracle.mimo_lut(xyz, 16, 16, 180.0)
+    p_mimo = oracle.mimo_update(g["window"], off[5:6], fr[5:6])[0]
+    p_beam = oracle.particle_beam(g["window"], off[5], fr[5])
+    assert np.isclose(p_beam / 64.0, p_mimo, rtol=1e-6)
+
+
+def test_cfg4_tables_golden(oracle, golden):
+    th, ph = cases.cfg4_targets()
+    xyz = oracle.create_tiled_antenna(cases.origins(4, 2))
+    off, fr = oracle.steer_tables(xyz, th, ph)
+    assert np.array_equal(off, golden["tables"]["cfg4_off"])
+    assert np.array_equal(fr, golden["tables"]["cfg4_frac"])
+
+
+def test_heatmap_calibrate_ingest_golden(oracle, golden):
+    g = golden["snapshot"]
+    heat, arg, mx = oracle.populate_heatmap(g["power"])
+    assert np.array_equal(heat, g["heat"]) and arg == int(g["heat_argmax"]) and mx == float(g["heat_max"])
+    assert heat.max() == 255 and heat[arg] == 255
+    cal = g["window"].copy()
+    cal[5] *= 0.0
+    cal[9] *= 3.0
+    cal[33] *= 0.5
+    idx, corr, med, mean = oracle.calibrate(cal)
+    assert np.array_equal(idx, g["cal_index"]) and np.array_equal(corr, g["cal_corr"])
+    assert med == float(g["cal_median"]) and mean == float(g["cal_mean"])
+    assert 5 not in idx          # dead microphone gated out (aw_processing_unit.cpp:166)
+    exposure = oracle.ingest(g["wire"])
+    assert np.array_equal(exposure, g["exposure"])
+    # un-flip + /2^23 restores the quantised signal
+    q = np.rint(g["window"][:, :64].astype(np.float64) * 8388608.0) / 8388608.0
+    assert np.array_equal(exposure, q.astype(np.float32))
+
+
+def test_empty_and_ragged_masks(oracle, golden):
+    g = golden["snapshot"]
+    xyz = oracle.create_antenna()
+    off, fr = oracle.mimo_lut(xyz, 4, 4, 90.0)
+    one = oracle.mimo_update(g["window"], off, fr, index=np.array([7], np.int32))
+    assert np.all(np.isfinite(one)) and one.max() > 0
+    rev = oracle.mimo_update(g["window"], off, fr, index=np.arange(63, -1, -1, dtype=np.int32))
+    fwd = oracle.mimo_update(g["window"], off, fr)
+    assert np.allclose(rev, fwd, rtol=1e-3)     # same physics, different rounding order
