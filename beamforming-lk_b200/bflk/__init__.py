@@ -29,7 +29,8 @@ SYMBOLS = [
     "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_batch",
-    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_launch_count", "bflk_miso", "bflk_miso_dev",
+    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
+    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
 ]
 
@@ -83,6 +84,9 @@ def load_library():
     L.bflk_set_kernel.argtypes = [vp, i32]
     L.bflk_launch_count.argtypes = [vp]
     L.bflk_launch_count.restype = i64
+    L.bflk_get_kernel.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.bflk_enable_timing.argtypes = [vp, i32]
+    L.bflk_kernel_time_ms.argtypes = [vp, C.POINTER(f32), C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
     L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.bflk_miso_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
@@ -148,6 +152,21 @@ class Beamformer:
 
     def launch_count(self):
         return int(self._L.bflk_launch_count(self._h))
+
+    def kernel_info(self):
+        """(last kernel used: 1 generic / 2 tiled, tile span, window chunks of the tiled variant)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._L.bflk_get_kernel(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def enable_timing(self, on=True):
+        self._check(self._L.bflk_enable_timing(self._h, 1 if on else 0))
+
+    def kernel_time_ms(self):
+        """(das_ms, das_launches, pack_ms, pack_launches) accumulated since the last call."""
+        a, b, c, d = C.c_float(), C.c_int32(), C.c_float(), C.c_int32()
+        self._check(self._L.bflk_kernel_time_ms(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
 
     # -- geometry / tables ------------------------------------------------------------------------------------
     def set_geometry(self, xyz):

@@ -78,7 +78,7 @@ int bflk_destroy(bflk_handle *h) {
         cudaStreamDestroy(h->stream);
     }
     h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
-    h->d_tile_dirs.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
+    h->d_tile_dirs.release(); h->d_packed.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release();
     delete h;
@@ -349,6 +349,56 @@ int bflk_set_kernel(bflk_handle *h, int32_t which) {
 
 int64_t bflk_launch_count(const bflk_handle *h) { return h ? h->launches : 0; }
 
+int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (last_used) *last_used = h->kernel_last;
+    if (tile_span) *tile_span = h->tiles_valid ? h->tile_smax : -1;
+    if (window_chunks) *window_chunks = (h->tiles_valid && h->tiles_usable) ? h->tile_geom.nch : 0;
+    return BFLK_OK;
+}
+
+static void timing_hook(void *ctx, int kind, bool begin, cudaStream_t st) {
+    bflk_handle *h = static_cast<bflk_handle *>(ctx);
+    if (!h->timing) return;
+    if (begin) {
+        bflk_handle::Timed t{};
+        t.kind = kind;
+        cudaEventCreate(&t.e0);
+        cudaEventCreate(&t.e1);
+        cudaEventRecord(t.e0, st);
+        h->timed.push_back(t);
+    } else if (!h->timed.empty()) {
+        cudaEventRecord(h->timed.back().e1, st);
+    }
+}
+
+int bflk_enable_timing(bflk_handle *h, int32_t on) {
+    if (!h) return BFLK_ERR_INVALID;
+    h->timing = on != 0;
+    return BFLK_OK;
+}
+
+int bflk_kernel_time_ms(bflk_handle *h, float *das_ms, int32_t *das_launches, float *pack_ms, int32_t *pack_launches) {
+    if (!h) return BFLK_ERR_INVALID;
+    float ms[2] = {0.f, 0.f};
+    int32_t n[2] = {0, 0};
+    for (auto &t : h->timed) {
+        float v = 0.f;
+        BFLK_CUDA(h, cudaEventSynchronize(t.e1));
+        BFLK_CUDA(h, cudaEventElapsedTime(&v, t.e0, t.e1));
+        ms[t.kind] += v;
+        n[t.kind]++;
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    h->timed.clear();
+    if (das_ms) *das_ms = ms[0];
+    if (das_launches) *das_launches = n[0];
+    if (pack_ms) *pack_ms = ms[1];
+    if (pack_launches) *pack_launches = n[1];
+    return BFLK_OK;
+}
+
 static int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
     return (int64_t)(n_frames - 1) * h->cfg.frame_len + h->cfg.history + h->cfg.frame_len + 1;
 }
@@ -365,19 +415,23 @@ static int ensure_tiles(bflk_handle *h) {
     const int tile_rows = (row1 - row0) / 2 + 1, tile_cols = (cols + 1) / 2;
     const int n_tiles = tile_rows * tile_cols;
     const int usable = (int)h->index.size();
-    BFLK_CUDA(h, h->d_tiles.reserve((size_t)n_tiles * usable));
+    BFLK_CUDA(h, h->d_tiles.reserve(tile_table_entries(n_tiles, usable)));
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, tile_table_entries(n_tiles, usable) * sizeof(TileEntry), h->stream));
     BFLK_CUDA(h, h->d_tile_dirs.reserve((size_t)n_tiles * 4));
     BFLK_CUDA(h, h->d_misc.reserve(4));
     BFLK_CUDA(h, h->p_misc.reserve(4));
     BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
+    const int stage_off = das_tile_geometry(h->cfg.history, h->max_delay, 0).stage_off;
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, h->d_tiles.p, h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
+                                    h->dir_first, h->dir_count, stage_off, h->d_tiles.p, h->d_tile_dirs.p, n_tiles,
+                                    h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[0];
-    h->tiles_usable = h->tile_smax <= das_tile_max_span();
+    h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax);
     return BFLK_OK;
 }
 
@@ -398,6 +452,7 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
         int rc = ensure_tiles(h);
         if (rc) return rc;
         tiled = h->tiles_usable;
+        if (tiled && (n_samples & 1)) tiled = false;  // packed rows are gathered with 8-byte loads
         if (h->kernel_choice == 2 && !tiled)
             return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
                            h->tile_smax, das_tile_max_span());
@@ -414,19 +469,21 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
         a.n_tiles = h->n_tiles;
         a.usable = usable;
         a.n_dir = h->dir_count;
-        a.min_base = h->cfg.history - h->max_delay;
-        a.max_reach = h->cfg.history;
+        a.index = h->d_index.p;
+        a.geom = h->tile_geom;
         a.power = power_dev;
         a.norm = norm;
-        a.smax = h->tile_smax;
+        BFLK_CUDA(h, h->d_packed.reserve(das_tile_packed_bytes(a)));
+        a.packed = h->d_packed.p;
         const int blocks_per_frame = N <= 256 ? 1 : (N - 2 + 253) / 254;
         if (blocks_per_frame > 1) {
             BFLK_CUDA(h, h->d_partial.reserve((size_t)n_frames * blocks_per_frame * h->dir_count));
             a.partial = h->d_partial.p;
         }
         int launches = 0;
-        BFLK_CUDA(h, launch_das_tile(a, h->sm_count, st, &launches));
+        BFLK_CUDA(h, launch_das_tile(a, h->sm_count, st, &launches, timing_hook, h));
         h->launches += launches;
+        h->kernel_last = 2;
     } else {
         GenericArgs a{};
         a.stream = stream_dev;
@@ -443,8 +500,11 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
         a.power = power_dev;
         a.audio = nullptr;
         a.norm = norm;
+        timing_hook(h, 0, true, st);
         BFLK_CUDA(h, launch_das_generic(a, st));
+        timing_hook(h, 0, false, st);
         h->launches++;
+        h->kernel_last = 1;
     }
     return BFLK_OK;
 }

@@ -23,11 +23,30 @@ struct DirTrig {
 // Packed per-(direction tile, usable channel) entry of the register-tiled kernel (das_tile.cu).
 // base: even-aligned smallest offset of the tile's directions, delta[r] = offset[r] - base.
 struct __align__(16) TileEntry {
-    int32_t base;       // window index of the first pair the warp loads (even)
-    uint32_t deltas;    // 4 x 8 bit: delta of direction r in bits [8r, 8r+8)
-    int32_t row;        // physical channel row in the sample stream
-    int32_t span;       // max delta (pairs of the shared window actually needed beyond K+1)
+    uint32_t win_off;   // byte offset of lane 0's window inside a packed row (padded layout)
+    uint32_t deltas;    // 4 x 6 bit: delta of direction r in bits [6r, 6r+6); bits 24-25: (first chunk) & 3
+    int32_t span;       // max delta of the tile for this channel
+    int32_t reserved;
     float frac[4];      // fractional delays of the 4 directions
+};
+
+// Tiling constants shared by the table builder (tables.cu) and the kernel (das_tile.cu).
+constexpr int kTileWarps = 12;  // direction tiles (= compute warps) per CTA
+constexpr int kTileCC = 16;     // channels per pipeline stage
+// Tile tables are stored per (tile group, stage) so that one bulk copy fetches a CTA's stage:
+// entry(tile t, channel slot s) = tiles[((t / kTileWarps) * n_stage + s / kTileCC) * kTileWarps * kTileCC
+//                                       + (t % kTileWarps) * kTileCC + s % kTileCC],  n_stage = ceil(usable / kTileCC).
+inline size_t tile_table_entries(int n_tiles, int usable) {
+    const size_t groups = (n_tiles + kTileWarps - 1) / kTileWarps, stages = (usable + kTileCC - 1) / kTileCC;
+    return groups * stages * kTileWarps * kTileCC;
+}
+
+// Shape of the packed rows the tiled kernel stages (das_tile.cu).
+struct TileGeometry {
+    int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
+    int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
+    int row_chunks = 0;  // logical chunks per packed row
+    int row_bytes = 0;   // padded bytes per packed row
 };
 
 template <typename T>
@@ -79,6 +98,7 @@ struct bflk_handle {
     std::string error;
     int64_t launches = 0;
     int kernel_choice = 0;  // 0 auto, 1 generic, 2 tiled
+    int kernel_last = 0;    // what the last power-map call ran
 
     // geometry + mask (host copies are the source of truth; device copies feed the table kernels)
     bool have_geometry = false;
@@ -102,8 +122,10 @@ struct bflk_handle {
     bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
     int32_t n_tiles = 0;
     int32_t tile_smax = 0;       // compiled window slack the tables need
-    bflk::DevBuf<bflk::TileEntry> d_tiles;  // [n_tiles][usable]
+    bflk::DevBuf<bflk::TileEntry> d_tiles;  // tile_table_entries(n_tiles, usable), layout above
     bflk::DevBuf<int32_t> d_tile_dirs;      // [n_tiles][4] local direction index (or -1)
+    bflk::TileGeometry tile_geom;
+    bflk::DevBuf<char> d_packed;            // pair-interleaved staging rows of the current batch
 
     // scratch
     bflk::DevBuf<float> d_window, d_power, d_audio, d_partial;
@@ -114,6 +136,11 @@ struct bflk_handle {
     bflk::PinBuf<float> p_in, p_out;
     bflk::PinBuf<bflk::DirTrig> p_trig;
     bflk::PinBuf<int32_t> p_misc;
+
+    // optional kernel timing (bflk_enable_timing): event pairs recorded on the launching stream
+    bool timing = false;
+    struct Timed { cudaEvent_t e0, e1; int kind; };  // kind 0: delay-and-sum kernel, 1: pack pre-pass
+    std::vector<Timed> timed;
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -143,8 +170,8 @@ cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d
 cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st);
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, TileEntry *d_tiles, int32_t *d_tile_dirs,
-                               int n_tiles, int32_t *d_maxspan, cudaStream_t st);
+                               int rows, int cols, int first, int count, int stage_off, TileEntry *d_tiles,
+                               int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
 struct GenericArgs {
@@ -172,20 +199,25 @@ struct TileArgs {
     int n_frames;
     int frame_len;
     int frame_stride;
-    const TileEntry *tiles;      // [n_tiles][usable]
+    const TileEntry *tiles;      // tile_table_entries() entries, grouped per (tile group, stage)
     const int32_t *tile_dirs;    // [n_tiles][4]
     int n_tiles;
     int usable;
     int n_dir;                   // directions in this handle's range (power row length)
-    int min_base;                // smallest TileEntry::base (window start to stage)
-    int max_reach;               // largest base + span (window end to stage, in samples beyond the block)
+    const int32_t *index;        // [usable] channel mask (pack gathers rows in this order)
+    TileGeometry geom;
+    void *packed;                // das_tile_packed_bytes() of scratch
     float *power;                // [B][n_dir]
-    float *partial;              // [B][blocks][n_dir] when frame_len > 256
+    float *partial;              // [B * blocks][n_dir] when frame_len > 256
     float norm;
-    int smax;
 };
-cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches);
+// hook(kind, begin): called right before (begin = true) and after each pack (kind 1) / main (kind 0) launch
+typedef void (*TileLaunchHook)(void *ctx, int kind, bool begin, cudaStream_t st);
+cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
+                            void *hook_ctx = nullptr);
 int das_tile_max_span();
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span);
+size_t das_tile_packed_bytes(const TileArgs &a);
 
 // ---- post.cu ----------------------------------------------------------------------------------------
 cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st);

@@ -1,6 +1,428 @@
-// das_tile.cu -- register-tiled full-grid power map (placeholder until the tiled kernel lands).
+// das_tile.cu -- register-tiled delay-and-sum power map for sm_100a (the hot kernel).
+//
+// Replaces the loop nest of MIMOWorker::update (src/dsp/mimo.cpp:121-150) around delay()
+// (src/dsp/delay.cpp:16-26).  Design (DESIGN.md "das_tile"):
+//
+//  * pack_kernel rewrites the channel-major stream once per batch into "pair-interleaved" rows:
+//    element g of a row is float2{ blockA[g], blockB[g] } for two 256-sample output blocks A and B,
+//    gathered in channel-mask order and laid out with one 16-byte pad every four 16-byte chunks.
+//    With that layout (a) one FFMA2/FADD2 (fma.rn.f32x2 / add.rn.f32x2) advances the same output
+//    sample of two blocks, for any delay parity, (b) a row is a contiguous byte range the main kernel
+//    stages with cp.async.bulk (TMA bulk copy) + mbarrier, and (c) the 64-byte lane stride of the
+//    per-thread windows becomes 80 bytes, which is bank-conflict-free for LDS.128.
+//  * das_tile_kernel: one warp = one 2x2 tile of steering directions x two 256-sample blocks; lane l
+//    owns output samples 8l..8l+7 of both blocks.  Per channel the warp loads ONE shared window of
+//    sample pairs into registers, forms the differences s[i]-s[i+1] once, and serves the four
+//    directions from registers through a warp-uniform switch on each direction's offset inside the
+//    window: 2 + 1/4 FP32 lane-operations per (direction, channel, sample) instead of 3, and ~0.4
+//    shared-memory words instead of >1.  Channels are accumulated sequentially in mask order with the
+//    reference's exact operation triple, so the delayed sums are bit-identical to the CPU path.
+//  * epilogue: 3-tap high-pass + squares (mimo.cpp:131-135) with neighbour samples from lane +-1,
+//    warp-shuffle reduction, one store per (block, direction).
+#include <cuda/std/cstdint>
+
 #include "bflk_internal.h"
+
 namespace bflk {
-int das_tile_max_span() { return -1; }
-cudaError_t launch_das_tile(const TileArgs &, int, cudaStream_t, int *) { return cudaErrorNotSupported; }
+
+namespace {
+
+constexpr int kWarps = kTileWarps;   // compute warps per CTA = direction tiles per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kCC = kTileCC;         // channels per pipeline stage
+constexpr int kStages = 3;
+constexpr int kBlock = 256;          // output samples per block
+constexpr int kK = 8;                // sample pairs per lane
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 dup2(float f) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(f));
+    return d;
+}
+__device__ __forceinline__ float lo(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+__device__ __forceinline__ void lds128(u64 &a, u64 &b, uint32_t addr) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// chunk (16 B = 2 sample pairs) c of a row lives at padded chunk c + (c >> 2)
+__host__ __device__ __forceinline__ int padded_chunk(int c) { return c + (c >> 2); }
+
+}  // namespace
+
+// ---- packed tile entry as the kernel reads it -----------------------------------------------------------
+// word0: byte offset of the warp's window inside a packed row (lane 0), word1: 4 x 6-bit deltas | r << 24,
+// word2: span, word3: unused; then the four fractions.
+static_assert(sizeof(TileEntry) == 32, "TileEntry is two 16-byte loads");
+
+// ---- pack: stream[C][T] -> packed[pair][usable][row] of float2{A, B} -------------------------------------
+struct PackArgs {
+    const float *stream;
+    int64_t row_stride;   // T
+    int n_frames, frame_len, frame_stride;
+    int blocks_per_frame;
+    int n_items;          // n_frames * blocks_per_frame
+    int pair0;            // first pair of this launch (grid.z is limited to 65535)
+    const int32_t *index;
+    int usable;
+    int stage_off;        // first staged sample relative to a block start (even)
+    int row_chunks;       // logical chunks per row
+    int row_bytes;        // padded bytes per row (multiple of 16)
+    float4 *packed;
+};
+
+__device__ __forceinline__ int64_t item_start(int item, int blocks_per_frame, int frame_len, int frame_stride) {
+    const int b = item / blocks_per_frame, q = item - b * blocks_per_frame;
+    const int s = min(254 * q, frame_len - kBlock);
+    return (int64_t)b * frame_stride + s;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+    const int pair = a.pair0 + blockIdx.z, s = blockIdx.y;
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= a.row_chunks) return;
+    const int itemA = 2 * pair, itemB = min(2 * pair + 1, a.n_items - 1);
+    const int64_t tA = item_start(itemA, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch;
+    const int64_t tB = item_start(itemB, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch;
+    const float *row = a.stream + (size_t)a.index[s] * a.row_stride;
+    float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
+    if (tA + 1 < a.row_stride) A = *reinterpret_cast<const float2 *>(row + tA);
+    else if (tA < a.row_stride) A.x = row[tA];
+    if (tB + 1 < a.row_stride) B = *reinterpret_cast<const float2 *>(row + tB);
+    else if (tB < a.row_stride) B.x = row[tB];
+    char *dst = reinterpret_cast<char *>(a.packed) + ((size_t)pair * a.usable + s) * a.row_bytes + 16 * padded_chunk(ch);
+    *reinterpret_cast<float4 *>(dst) = make_float4(A.x, B.x, A.y, B.y);
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------------
+struct KernelArgs {
+    const char *packed;          // [pair][usable][row_bytes]
+    const TileEntry *tiles;      // grouped per (tile group, stage), see tile_table_entries()
+    const int32_t *tile_dirs;    // [n_tiles][4]
+    int n_tiles, usable, n_dir;
+    int row_bytes;
+    int n_items, blocks_per_frame, frame_len;
+    int pair0;
+    float *out;                  // power [frames][n_dir] (blocks_per_frame == 1) or partial [items][n_dir]
+    float norm;
+};
+
+template <int NCH>
+struct Window {
+    u64 w[2 * NCH];
+};
+
+// loads the NCH chunks of this lane's window; R = (first chunk index) & 3 fixes where the pad chunks fall
+template <int NCH, int R>
+__device__ __forceinline__ void load_window(u64 (&w)[2 * NCH], uint32_t addr) {
+#pragma unroll
+    for (int m = 0; m < NCH; m++) lds128(w[2 * m], w[2 * m + 1], addr + 16 * (m + ((R + m) >> 2)));
+}
+
+// acc[k] += fma(f, d[D + k], w[D + k + 1]) for the 8 sample pairs of this lane (delay.cpp:24)
+template <int NCH, int D>
+__device__ __forceinline__ void accumulate(u64 (&acc)[kK], const u64 (&w)[2 * NCH], const u64 (&d)[2 * NCH - 1], u64 ff) {
+#pragma unroll
+    for (int k = 0; k < kK; k++) acc[k] = add2(acc[k], fma2(ff, d[D + k], w[D + k + 1]));
+}
+
+template <int NCH>
+__device__ __forceinline__ void accumulate_dyn(int delta, u64 (&acc)[kK], const u64 (&w)[2 * NCH], const u64 (&d)[2 * NCH - 1],
+                                               float f) {
+    const u64 ff = dup2(f);
+    constexpr int kMax = 2 * NCH - 9;  // largest delta whose window still fits the loaded chunks
+    switch (delta) {
+#define BFLK_CASE(D) \
+    case D:          \
+        if constexpr (D <= kMax) accumulate<NCH, (D <= kMax ? D : 0)>(acc, w, d, ff); \
+        break;
+        BFLK_CASE(0) BFLK_CASE(1) BFLK_CASE(2) BFLK_CASE(3) BFLK_CASE(4) BFLK_CASE(5) BFLK_CASE(6) BFLK_CASE(7)
+        BFLK_CASE(8) BFLK_CASE(9) BFLK_CASE(10) BFLK_CASE(11)
+#undef BFLK_CASE
+        default: break;
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kThreads, 1) das_tile_kernel(KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * 32 } then barriers
+    const int stage_rows = kCC * a.row_bytes;
+    const int stage_bytes = stage_rows + kWarps * kCC * (int)sizeof(TileEntry);
+    const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages], empty[kStages]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = a.pair0 + blockIdx.y;
+    const int tile0 = blockIdx.x * kWarps;
+    const int my_tile = min(tile0 + warp, a.n_tiles - 1);
+    const bool active = tile0 + warp < a.n_tiles;  // idle warps of the last tile group only keep the pipeline moving
+    const int n_stage = (a.usable + kCC - 1) / kCC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (kStages + s), kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const char *rows_g = a.packed + (size_t)pair * a.usable * a.row_bytes;
+    auto issue = [&](int st) {  // producer: one thread fills buffer st % kStages with channel chunk st
+        const int buf = st % kStages;
+        const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
+        const uint32_t dst = smem + buf * stage_bytes;
+        const uint32_t full = bars + 8 * buf;
+        constexpr uint32_t tile_bytes = kWarps * kCC * (uint32_t)sizeof(TileEntry);
+        mbar_expect_tx(full, (uint32_t)(nc * a.row_bytes) + tile_bytes);
+        bulk_g2s(dst, rows_g + (size_t)c0 * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
+        bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC), tile_bytes, full);
+    };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < min(kStages - 1, n_stage); st++) issue(st);
+    }
+
+    u64 acc[4][kK];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < kK; k++) acc[r][k] = 0ull;
+
+    const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
+    for (int st = 0; st < n_stage; st++) {
+        const int buf = st % kStages;
+        // refill the buffer every warp left one stage ago with the chunk two stages ahead
+        if (threadIdx.x == 0 && st + kStages - 1 < n_stage) {
+            if (st >= 1) mbar_wait(bars + 8 * (kStages + (st - 1) % kStages), ((st - 1) / kStages) & 1);
+            issue(st + kStages - 1);
+        }
+        mbar_wait(bars + 8 * buf, (st / kStages) & 1);
+        const uint32_t rows_s = smem + buf * stage_bytes;
+        const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * (int)sizeof(TileEntry);
+        const int nc = min(kCC, a.usable - st * kCC);
+        for (int c = 0; active && c < nc; c++) {
+            uint32_t e0, e1, e2, e3;
+            float f0, f1, f2, f3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(tiles_s + 32 * c));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(tiles_s + 32 * c + 16));
+            const uint32_t addr = rows_s + c * a.row_bytes + e0 + lane_off;
+            u64 w[2 * NCH];
+            switch (e1 >> 24) {
+                case 0: load_window<NCH, 0>(w, addr); break;
+                case 1: load_window<NCH, 1>(w, addr); break;
+                case 2: load_window<NCH, 2>(w, addr); break;
+                default: load_window<NCH, 3>(w, addr); break;
+            }
+            u64 d[2 * NCH - 1];
+#pragma unroll
+            for (int j = 0; j < 2 * NCH - 1; j++) d[j] = sub2(w[j], w[j + 1]);  // s[i] - s[i+1], once per window
+            accumulate_dyn<NCH>(e1 & 63, acc[0], w, d, f0);
+            accumulate_dyn<NCH>((e1 >> 6) & 63, acc[1], w, d, f1);
+            accumulate_dyn<NCH>((e1 >> 12) & 63, acc[2], w, d, f2);
+            accumulate_dyn<NCH>((e1 >> 18) & 63, acc[3], w, d, f3);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (kStages + buf));
+    }
+
+    // ---- epilogue: MA = 0.5 out[j] - 0.25 (out[j+1] + out[j-1]); power = sum MA^2 (mimo.cpp:131-137) ----
+    const int itemA = 2 * pair, itemB = 2 * pair + 1;
+    int jlo[2], jhi[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int item = min(h ? itemB : itemA, a.n_items - 1);
+        const int q = item % a.blocks_per_frame;
+        const int s = min(254 * q, a.frame_len - kBlock);
+        jlo[h] = 254 * q + 1 - s;
+        jhi[h] = min(254 * q + 254, a.frame_len - 2) - s;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        u64 prev = __shfl_up_sync(0xffffffffu, acc[r][kK - 1], 1);
+        u64 next = __shfl_down_sync(0xffffffffu, acc[r][0], 1);
+        float pa = 0.f, pb = 0.f;
+#pragma unroll
+        for (int k = 0; k < kK; k++) {
+            const u64 left = k == 0 ? prev : acc[r][k - 1];
+            const u64 right = k == kK - 1 ? next : acc[r][k + 1];
+            const int j = kK * lane + k;
+            float ma = __fsub_rn(__fmul_rn(lo(acc[r][k]), 0.5f), __fmul_rn(0.25f, __fadd_rn(lo(right), lo(left))));
+            float mb = __fsub_rn(__fmul_rn(hi(acc[r][k]), 0.5f), __fmul_rn(0.25f, __fadd_rn(hi(right), hi(left))));
+            if (j >= jlo[0] && j <= jhi[0]) pa = __fmaf_rn(ma, ma, pa);
+            if (j >= jlo[1] && j <= jhi[1]) pb = __fmaf_rn(mb, mb, pb);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pa += __shfl_xor_sync(0xffffffffu, pa, o);
+            pb += __shfl_xor_sync(0xffffffffu, pb, o);
+        }
+        if (lane == 0 && active) {
+            const int dir = a.tile_dirs[4 * my_tile + r];
+            if (dir >= 0) {
+                if (a.blocks_per_frame == 1) {
+                    a.out[(size_t)itemA * a.n_dir + dir] = __fdiv_rn(pa, a.norm);
+                    if (itemB < a.n_items) a.out[(size_t)itemB * a.n_dir + dir] = __fdiv_rn(pb, a.norm);
+                } else {
+                    a.out[(size_t)itemA * a.n_dir + dir] = pa;
+                    if (itemB < a.n_items) a.out[(size_t)itemB * a.n_dir + dir] = pb;
+                }
+            }
+        }
+    }
+}
+
+// frames longer than one block: power[b][d] = (sum_q partial[b*nblk + q][d]) / norm, blocks in order
+__global__ void finalize_kernel(const float *__restrict__ partial, int n_frames, int nblk, int n_dir, float norm,
+                                float *__restrict__ power) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (d >= n_dir) return;
+    float p = 0.f;
+    for (int q = 0; q < nblk; q++) p += partial[((size_t)b * nblk + q) * n_dir + d];
+    power[(size_t)b * n_dir + d] = __fdiv_rn(p, norm);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+int das_tile_max_span() { return 11; }
+
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span) {
+    TileGeometry g;
+    g.stage_off = (history - max_delay) & ~1;
+    g.nch = max_span <= 3 ? 6 : (max_span <= 7 ? 8 : 10);
+    // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
+    g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
+    g.row_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
+    return g;
+}
+
+template <int NCH>
+static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    das_tile_kernel<NCH><<<grid, kThreads, smem, st>>>(k);
+    return cudaGetLastError();
+}
+
+size_t das_tile_packed_bytes(const TileArgs &a) {
+    const int nblk = a.frame_len <= kBlock ? 1 : (a.frame_len - 2 + 253) / 254;
+    const int n_items = a.n_frames * nblk;
+    return (size_t)((n_items + 1) / 2) * a.usable * a.geom.row_bytes;
+}
+
+cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook, void *hook_ctx) {
+    (void)sm_count;
+    const int nblk = a.frame_len <= kBlock ? 1 : (a.frame_len - 2 + 253) / 254;
+    const int n_items = a.n_frames * nblk;
+    const int n_pairs = (n_items + 1) / 2;
+    if (a.frame_len < kBlock || (a.row_stride & 1) || (a.frame_stride & 1) || (a.frame_len & 1)) return cudaErrorInvalidValue;
+
+    PackArgs p{};
+    p.stream = a.stream;
+    p.row_stride = a.row_stride;
+    p.n_frames = a.n_frames;
+    p.frame_len = a.frame_len;
+    p.frame_stride = a.frame_stride;
+    p.blocks_per_frame = nblk;
+    p.n_items = n_items;
+    p.index = a.index;
+    p.usable = a.usable;
+    p.stage_off = a.geom.stage_off;
+    p.row_chunks = a.geom.row_chunks;
+    p.row_bytes = a.geom.row_bytes;
+    p.packed = reinterpret_cast<float4 *>(a.packed);
+    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * sizeof(TileEntry)) + 2 * kStages * 8;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+
+    KernelArgs k{};
+    k.packed = reinterpret_cast<const char *>(a.packed);
+    k.tiles = a.tiles;
+    k.tile_dirs = a.tile_dirs;
+    k.n_tiles = a.n_tiles;
+    k.usable = a.usable;
+    k.n_dir = a.n_dir;
+    k.row_bytes = a.geom.row_bytes;
+    k.n_items = n_items;
+    k.blocks_per_frame = nblk;
+    k.frame_len = a.frame_len;
+    k.out = nblk == 1 ? a.power : a.partial;
+    k.norm = a.norm;
+
+    // grid.y / grid.z are limited to 65535: process the pairs in slabs
+    const int max_slab = 32768;
+    for (int p0 = 0; p0 < n_pairs; p0 += max_slab) {
+        const int np = min(max_slab, n_pairs - p0);
+        PackArgs ps = p;
+        KernelArgs ks = k;
+        ps.pair0 = p0;
+        ks.pair0 = p0;
+        dim3 pg((a.geom.row_chunks + 255) / 256, a.usable, np);
+        if (hook) hook(hook_ctx, 1, true, st);
+        pack_kernel<<<pg, 256, 0, st>>>(ps);
+        if (hook) hook(hook_ctx, 1, false, st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        dim3 grid((a.n_tiles + kWarps - 1) / kWarps, np);
+        if (hook) hook(hook_ctx, 0, true, st);
+        switch (a.geom.nch) {
+            case 6: e = launch_main<6>(ks, grid, smem, st); break;
+            case 8: e = launch_main<8>(ks, grid, smem, st); break;
+            default: e = launch_main<10>(ks, grid, smem, st); break;
+        }
+        if (hook) hook(hook_ctx, 0, false, st);
+        if (e != cudaSuccess) return e;
+        *launches += 2;
+    }
+    if (nblk > 1) {
+        dim3 fg((a.n_dir + 255) / 256, a.n_frames);
+        finalize_kernel<<<fg, 256, 0, st>>>(a.partial, a.n_frames, nblk, a.n_dir, a.norm, a.power);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace bflk

@@ -90,8 +90,9 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // touches and directions outside the range get tile_dirs = -1 (computed but not stored).
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
-                                   int count, TileEntry *__restrict__ tiles, int32_t *__restrict__ tile_dirs,
-                                   int n_tiles, int tile_cols, int row0, int32_t *__restrict__ maxspan) {
+                                   int count, int stage_off, TileEntry *__restrict__ tiles,
+                                   int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
+                                   int32_t *__restrict__ maxspan) {
     const int t = blockIdx.x;
     if (t >= n_tiles) return;
     const int tr = t / tile_cols, tc = t % tile_cols;
@@ -122,21 +123,24 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
         }
         int mn = min(min(o[0], o[1]), min(o[2], o[3]));
         int base = mn & ~1;  // even: the pair-interleaved window is fetched with 16-byte loads
+        const int cb = (base - stage_off) >> 1;  // first 16-byte chunk of lane 0's window
         TileEntry e;
-        e.base = base;
-        e.row = c;
-        unsigned packed = 0;
+        e.win_off = 16u * (unsigned)(cb + (cb >> 2));  // one pad chunk after every four
+        e.reserved = 0;
+        unsigned packed = (unsigned)(cb & 3) << 24;
         int span = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             int dlt = o[q] - base;
             span = max(span, dlt);
-            packed |= (unsigned)(dlt & 0xff) << (8 * q);
+            packed |= (unsigned)(dlt & 63) << (6 * q);
             e.frac[q] = f[q];
         }
         e.deltas = packed;
         e.span = span;
-        tiles[(size_t)t * usable + s] = e;
+        const int n_stage = (usable + kTileCC - 1) / kTileCC;
+        tiles[((size_t)(t / kTileWarps) * n_stage + s / kTileCC) * (kTileWarps * kTileCC) + (t % kTileWarps) * kTileCC +
+              s % kTileCC] = e;
         span_max = max(span_max, span);
     }
     for (int o = 16; o > 0; o >>= 1) span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o));
@@ -144,12 +148,12 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 }
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, TileEntry *d_tiles, int32_t *d_tile_dirs,
-                               int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
+                               int rows, int cols, int first, int count, int stage_off, TileEntry *d_tiles,
+                               int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
-    build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, d_tiles,
-                                                d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+    build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
+                                                d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- full-grid delay-and-sum power maps per second on B200 (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--frames B] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of B synthetic frames (C channels x (B+3)*N samples,
+larger than L2) for every direction of the grid.  N = 1 runs the configuration the target is quoted on
+(cfg3: 512 microphones x 32x32 = 1024 directions x 256-sample frames).  N > 1 (torchrun, one rank per GPU)
+shards the steering grid across ranks -- total work fixed, "strong" scaling -- and assembles the
+per-rank power-map slices with an NCCL all-gather inside the timed region.
+
+One JSON line on rank 0.  `value`: maps/s with inputs resident in HBM.  `e2e`: the same through the
+host-buffer C-ABI call (H2D of the batch + D2H of the maps inside the timed region).  `roofline`: the
+dominant kernel (das_tile) against the FP32-FMA roofline the path is bound by, `roofline_hbm` against the
+measured copy bandwidth.  `cpu_baseline`: the compiled reference delay() loop (oracle/_ref) on the host.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "beamforming-lk_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+import cases  # noqa: E402
+
+METRIC = "power_maps_per_sec"
+UNIT = "maps/s"
+FP32_LANES_PER_SM = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=list(cases.CONFIGS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step (default: sized so the input exceeds L2)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def default_frames(c):
+    # input stream = C x (B + 3) x N floats; 268 MB at cfg3 with B = 512 (L2 is 126 MB)
+    C = 64 * c["nx"] * c["ny"]
+    per_frame = C * c["N"] * 4
+    return max(2, int(np.ceil(256e6 / per_frame)))
+
+
+def workload(c, name, B):
+    C = 64 * c["nx"] * c["ny"]
+    D = c["rows"] * c["cols"]
+    T = (B - 1) * c["N"] + c["W"]
+    T += T & 1
+    return dict(workload=f"{name}: {C} mics x {c['rows']}x{c['cols']}={D} directions x {c['N']}-sample frames",
+                channels=C, directions=D, frame_len=c["N"], frames_per_step=B, samples_per_channel=T,
+                input_mb=round(C * T * 4 / 1e6, 1), l2="inputs larger than L2 (126 MB); no flush needed")
+
+
+def flops_per_map(C, D, N):
+    return D * N * (4 * C + 6)          # 4 FLOP per (dir, ch, sample) + 6 per (dir, sample)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.stop = index, [], set(), threading.Event()
+        self.max_mhz = None
+        self.thread = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            while not self.stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # NVML unavailable: report that rather than fail the bench
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def make_input(c, T):
+    from bflk import synth
+    xyz = synth.tile_geometry(cases.origins(c["nx"], c["ny"]))
+    # tones are cheap, white noise for 512 x 132k samples is not: tile a 16-frame noise block
+    base = synth.make_stream(xyz, T, sigma=0.0)
+    rng = np.random.Generator(np.random.Philox(synth.SEED))
+    blk = (1e-3 * rng.standard_normal((xyz.shape[0], 16 * c["N"]))).astype(np.float32)
+    reps = int(np.ceil(T / blk.shape[1]))
+    base += np.tile(blk, (1, reps))[:, :T]
+    return np.ascontiguousarray(base, np.float32)
+
+
+def cpu_reference_rate(c, stream, n_threads, budget_s, frames=None):
+    """maps/s of the compiled reference delay() loop (oracle/_ref) over all directions, n_threads threads."""
+    from oracle import oracle as O
+    if O.ref() is None:
+        raise RuntimeError("oracle/_ref/libref.so is missing")
+    xyz = O.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    off, fr = O.mimo_lut(xyz, c["rows"], c["cols"], c["fov"], c["H"])
+    D = off.shape[0]
+    sub = 1
+    est_units = D * xyz.shape[0] * c["N"]
+    if est_units / (1.5e9 * n_threads) > budget_s / 3:      # cfg5: time a direction subset and scale
+        sub = int(np.ceil(est_units / (1.5e9 * n_threads) / (budget_s / 3)))
+        off, fr = np.ascontiguousarray(off[::sub]), np.ascontiguousarray(fr[::sub])
+    window = np.ascontiguousarray(stream[:, :c["W"]])
+    O.ref_mimo_update(window, off, fr, n=c["N"], n_threads=n_threads)      # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        b = done % max(1, (stream.shape[1] - c["W"]) // c["N"] + 1)
+        window = np.ascontiguousarray(stream[:, b * c["N"]: b * c["N"] + c["W"]])
+        O.ref_mimo_update(window, off, fr, n=c["N"], n_threads=n_threads)
+        done += 1
+        el = time.perf_counter() - t0
+        if (frames and done >= frames) or (not frames and el > budget_s):
+            break
+    rate = done / el / sub
+    sample = f"{done} frames x {off.shape[0]} of {D} directions in {el:.2f} s" + (f" (1/{sub} direction subset, scaled)" if sub > 1 else "")
+    return rate, sample
+
+
+def run_reference(args, c, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.frames or default_frames(c)
+    n_threads = os.cpu_count() or 1
+    T = 15 * c["N"] + c["W"]
+    stream = make_input(c, T)
+    frames_per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference_rate(c, stream, n_threads, 1e9, frames=1)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, sample = cpu_reference_rate(c, stream, n_threads, 1e9, frames=frames_per_step)
+        rates.append(r)
+    el = time.perf_counter() - t0
+    value = statistics.median(rates)
+    cfg = workload(c, name, B)
+    cfg["parallelism"] = f"{n_threads} host threads over directions"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "reference",
+                             "sample": f"each step = {frames_per_step} frames of the workload; last: {sample}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "dir_samples_per_sec": value * cfg["directions"] * c["N"]}
+    print(json.dumps(line))
+
+
+def run_ours(args, c, name):
+    import torch
+    import torch.distributed as dist
+    import bflk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.frames or default_frames(c)
+    C, D, N = 64 * c["nx"] * c["ny"], c["rows"] * c["cols"], c["N"]
+    cfg = workload(c, name, B)
+    T = cfg["samples_per_channel"]
+    if D % world:
+        raise SystemExit("grid does not divide across ranks")
+    per = D // world
+
+    w = bflk.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"], device=local,
+                        frame_len=N, history=c["H"], window_len=c["W"])
+    w.set_kernel(args.kernel)
+    w.set_direction_range(rank * per, per)
+
+    host_in = torch.from_numpy(make_input(c, T)).pin_memory()
+    stream_dev = host_in.to(dev, non_blocking=True)
+    local_pow = torch.empty((B, per), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, B, per), dtype=torch.float32, device=dev) if world > 1 else None
+    host_out = torch.empty((B, D), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    cs = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        w.power_map_batch_dev(stream_dev.data_ptr(), T, B, local_pow.data_ptr(), cs)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_pow)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput, dominant-kernel time and clocks over the timed region ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    w.enable_timing(True)
+    w.kernel_time_ms()
+    l0 = w.launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(step, args.steps, 0)
+    launches = w.launch_count() - l0
+    das_ms, das_n, pack_ms, pack_n = w.kernel_time_ms()
+    w.enable_timing(False)
+    value = B * args.steps / (ms / 1e3)
+    kinfo = w.kernel_info()
+
+    # ---- end to end: host buffers through the C ABI (N = 1) / pinned copies + gather (N > 1) ----
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            def e2e_step():
+                w.power_map_batch_ptr(host_in.data_ptr(), T, B, host_out.data_ptr())
+        else:
+            full = gathered
+
+            def e2e_step():
+                stream_dev.copy_(host_in, non_blocking=True)
+                step()
+                host_out.view(B, world, per).copy_(full.permute(1, 0, 2), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        e2e_steps = max(3, args.steps // 3)
+        barrier()
+        t0 = time.perf_counter()
+        ems = timed(e2e_step, e2e_steps, 1)
+        e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": C * T * 4,
+               "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
+               "path": "bflk_power_map_batch (host buffers)" if world == 1 else "pinned H2D + bflk_power_map_batch_dev + all_gather + D2H"}
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        clocks = clk.summary()
+        max_mhz = pk.get("sm_max_mhz") or clocks["sm_max_mhz"] or 1965.0
+        peak_tf = sm_count * FP32_LANES_PER_SM * 2 * max_mhz * 1e6 / 1e12
+        # algorithmic FLOPs one das launch performs on this rank: B maps x per directions
+        fl = flops_per_map(C, per, N) * B
+        das_avg_s = das_ms / 1e3 / max(1, das_n)
+        achieved_tf = fl / das_avg_s / 1e12 if das_n else None
+        alg_bytes = 4 * C * T + 4 * B * per
+        roof = {"bound": "fp32", "kernel": "das_tile" if kinfo[0] == 2 else "das_generic", "achieved": achieved_tf,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if achieved_tf else None,
+                "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz {max_mhz:.0f} ({pk_kind} MEASURED_PEAKS.json clock)",
+                "frac_at_sampled_clock": (achieved_tf / (peak_tf * clocks["sm_mhz"] / max_mhz)) if achieved_tf and clocks["sm_mhz"] else None,
+                "flop_per_launch": fl, "avg_launch_ms": das_avg_s * 1e3, "launches_timed": das_n,
+                "kernel_share_of_step": das_ms / ms, "pack_share_of_step": pack_ms / ms, "traffic": None}
+        roof_hbm = {"bound": "hbm", "achieved": alg_bytes / das_avg_s / 1e9 if das_n else None, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
+                    "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
+        cfg.update(parallelism=f"direction-sharded x{world}" if world > 1 else "single GPU", directions_per_gpu=per,
+                   kernel=roof["kernel"], tile_span=kinfo[1], window_chunks=kinfo[2])
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm,
+                "dir_samples_per_sec": value * D * N, "tflops_whole_job": value * flops_per_map(C, D, N) / 1e12}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                n_threads = os.cpu_count() or 1
+                rate, sample = cpu_reference_rate(c, host_in.numpy()[:, :16 * N + c["W"]], n_threads, budget_s=3.0)
+                rate1, sample1 = cpu_reference_rate(c, host_in.numpy()[:, :16 * N + c["W"]], 1, budget_s=2.0)
+                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n_threads, "kind": "reference",
+                                        "sample": sample, "single_thread_value": rate1, "single_thread_sample": sample1}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    c = cases.CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, c, args.config)
+    else:
+        run_ours(args, c, args.config)
+
+
+if __name__ == "__main__":
+    main()

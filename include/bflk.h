@@ -17,6 +17,7 @@
  *   bflk_set_grid_tables            the same LUT supplied by the caller (offsetDelays / fractionalDelays, mimo.h:86-89)
  *   bflk_steer_tables               Particle::steer (src/dsp/particle.cpp:37-49)
  *   bflk_power_map*                 MIMOWorker::update (src/dsp/mimo.cpp:97-151) -> powerdB
+ *   bflk_enable_timing / bflk_kernel_time_ms / bflk_launch_count   (no reference counterpart: measurement hooks)
  *   bflk_miso*                      Particle::steer + Particle::das + Particle::beam
  *                                   (src/dsp/particle.cpp:37-103) as used by MISOWorker::update (miso.cpp:39-46)
  *   bflk_heatmap                    MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95)
@@ -102,8 +103,17 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
                              float *power_dev, void *cuda_stream);
 /* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel. */
 int bflk_set_kernel(bflk_handle *h, int32_t which);
+/* Which kernel the last power-map call used (1 generic, 2 tiled; 0 = none yet), the largest offset spread
+ * inside a 2x2 direction tile for the current grid, and the window chunks of the tiled variant in use. */
+int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t bflk_launch_count(const bflk_handle *h);
+/* Kernel timing for the roofline report: when enabled, every launch of the dominant delay-and-sum kernel
+ * (and of the pack pre-pass) is bracketed by CUDA events on the stream it is launched on.
+ * bflk_kernel_time_ms synchronises on those events, returns the accumulated milliseconds and launch
+ * counts since the last call, and resets the accumulators. */
+int bflk_enable_timing(bflk_handle *h, int32_t on);
+int bflk_kernel_time_ms(bflk_handle *h, float *das_ms, int32_t *das_launches, float *pack_ms, int32_t *pack_launches);
 
 /* ---- dynamic steering (MISO) --------------------------------------------------------------------- */
 /* For each target t: steer(theta[t], phi[t]); audio_out[t][N] = Particle::das; power_out[t] = Particle::beam.
