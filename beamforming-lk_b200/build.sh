@@ -6,9 +6,9 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-ffp-contract=off ${EXTRA_NVCC_FLAGS:-}"
 mkdir -p build
 objs=()
-for f in csrc/bflk_api.cu csrc/tables.cu csrc/das_generic.cu csrc/das_tile.cu csrc/post.cu; do
+for f in csrc/bflk_api.cu csrc/tables.cu csrc/das_generic.cu csrc/das_tile.cu csrc/das_bcast.cu csrc/post.cu; do
   o=build/$(basename "${f%.cu}").o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/bflk_internal.h -nt "$o" ] || [ ../include/bflk.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/bflk_internal.h -nt "$o" ] || [ csrc/das_common.cuh -nt "$o" ] || [ ../include/bflk.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi
   objs+=("$o")

@@ -78,7 +78,7 @@ int bflk_destroy(bflk_handle *h) {
         cudaStreamDestroy(h->stream);
     }
     h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
-    h->d_tile_dirs.release(); h->d_packed.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
+    h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release();
     delete h;
@@ -89,6 +89,7 @@ int bflk_destroy(bflk_handle *h) {
 static void invalidate_tables(bflk_handle *h) {
     h->have_grid = false;
     h->tiles_valid = false;
+    h->bcast_valid = false;
     h->n_dir = 0;
     h->dir_first = h->dir_count = 0;
 }
@@ -151,6 +152,7 @@ int bflk_set_channel_mask(bflk_handle *h, const int32_t *index, int32_t usable) 
     }
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
     h->index = idx;
+    h->bcast_valid = false;
     BFLK_CUDA(h, h->d_index.reserve(idx.size()));
     BFLK_CUDA(h, cudaMemcpyAsync(h->d_index.p, h->index.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -291,6 +293,7 @@ int bflk_set_direction_range(bflk_handle *h, int32_t first, int32_t count) {
     h->dir_first = first;
     h->dir_count = count;
     h->tiles_valid = false;
+    h->bcast_valid = false;
     return BFLK_OK;
 }
 
@@ -342,7 +345,7 @@ int bflk_steer_tables(bflk_handle *h, const double *theta, const double *phi, in
 // ---- power map ---------------------------------------------------------------------------------------------
 int bflk_set_kernel(bflk_handle *h, int32_t which) {
     if (!h) return BFLK_ERR_INVALID;
-    if (which < 0 || which > 2) return h->fail(BFLK_ERR_INVALID, "bflk_set_kernel: %d", which);
+    if (which < 0 || which > 3) return h->fail(BFLK_ERR_INVALID, "bflk_set_kernel: %d", which);
     h->kernel_choice = which;
     return BFLK_OK;
 }
@@ -415,23 +418,84 @@ static int ensure_tiles(bflk_handle *h) {
     const int tile_rows = (row1 - row0) / 2 + 1, tile_cols = (cols + 1) / 2;
     const int n_tiles = tile_rows * tile_cols;
     const int usable = (int)h->index.size();
-    BFLK_CUDA(h, h->d_tiles.reserve(tile_table_entries(n_tiles, usable)));
-    BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, tile_table_entries(n_tiles, usable) * sizeof(TileEntry), h->stream));
     BFLK_CUDA(h, h->d_tile_dirs.reserve((size_t)n_tiles * 4));
     BFLK_CUDA(h, h->d_misc.reserve(4));
     BFLK_CUDA(h, h->p_misc.reserve(4));
-    BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
     const int stage_off = das_tile_geometry(h->cfg.history, h->max_delay, 0).stage_off;
+    // pass 1: largest offset spread inside a tile -> which kernel variant (window chunks, warps per CTA)
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, stage_off, h->d_tiles.p, h->d_tile_dirs.p, n_tiles,
+                                    h->dir_first, h->dir_count, stage_off, 1, nullptr, h->d_tile_dirs.p, n_tiles,
                                     h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[0];
-    h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
     h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax);
+    h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
+    if (!h->tiles_usable) return BFLK_OK;
+    // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
+    const size_t entries = tile_table_entries(n_tiles, usable, h->tile_geom.warps);
+    BFLK_CUDA(h, h->d_tiles.reserve(entries));
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * sizeof(TileEntry), h->stream));
+    BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
+                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.warps, h->d_tiles.p,
+                                    h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+// Builds (once per grid / mask / range) the direction tiles and per-lane tables of the lane-broadcast kernel.
+static int ensure_bcast(bflk_handle *h) {
+    if (h->bcast_valid) return BFLK_OK;
+    const int first = h->dir_first, count = h->dir_count;
+    std::vector<int32_t> globals;
+    if (h->rows > 0 && h->cols > 0) {
+        // 32 directions per tile; the narrow tile side runs along the array's longer axis, where
+        // neighbouring directions differ most in delay
+        float minx = 1e30f, maxx = -1e30f, miny = 1e30f, maxy = -1e30f;
+        for (size_t c = 0; c < h->xyz.size() / 3; c++) {
+            minx = std::min(minx, h->xyz[3 * c]); maxx = std::max(maxx, h->xyz[3 * c]);
+            miny = std::min(miny, h->xyz[3 * c + 1]); maxy = std::max(maxy, h->xyz[3 * c + 1]);
+        }
+        const int TR = (maxx - minx >= maxy - miny) ? 8 : 4, TC = 32 / TR;
+        const int cols = h->cols, r0 = first / cols, r1 = (first + count - 1) / cols;
+        for (int r = r0; r <= r1; r += TR)
+            for (int c = 0; c < cols; c += TC) {
+                int32_t t[32];
+                bool any = false;
+                for (int q = 0; q < 32; q++) {
+                    const int rr = r + q / TC, cc = c + q % TC;
+                    const int g = (rr < h->rows && cc < cols) ? rr * cols + cc : -1;
+                    t[q] = (g >= first && g < first + count) ? g : -1;
+                    any |= t[q] >= 0;
+                }
+                if (!any) continue;
+                std::stable_partition(t, t + 32, [](int32_t v) { return v >= 0; });  // valid directions first
+                globals.insert(globals.end(), t, t + 32);
+            }
+    } else {
+        for (int g0 = first; g0 < first + count; g0 += 32)
+            for (int q = 0; q < 32; q++) globals.push_back(g0 + q < first + count ? g0 + q : -1);
+    }
+    const int n_tiles = (int)(globals.size() / 32);
+    std::vector<int32_t> locals(globals.size());
+    for (size_t i = 0; i < globals.size(); i++) locals[i] = globals[i] >= 0 ? globals[i] - first : -1;
+    const int usable = (int)h->index.size();
+    h->bcast_geom = das_bcast_geometry(h->cfg.history, h->max_delay);
+    BFLK_CUDA(h, h->d_bcast_globals.reserve(globals.size()));
+    BFLK_CUDA(h, h->d_bcast_dirs.reserve(globals.size()));
+    BFLK_CUDA(h, h->d_bcast_table.reserve(das_bcast_table_entries(n_tiles, usable)));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_bcast_globals.p, globals.data(), globals.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_bcast_dirs.p, locals.data(), locals.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_bcast_table(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->d_bcast_globals.p,
+                                    n_tiles, h->bcast_geom, h->d_bcast_table.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
+    h->bcast_tiles = n_tiles;
+    h->bcast_valid = true;
     return BFLK_OK;
 }
 
@@ -447,6 +511,40 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const int N = h->cfg.frame_len, C = h->cfg.n_channels, usable = (int)h->index.size();
     const float norm = static_cast<float>(N * usable);  // power /= float(N_SAMPLES * count), mimo.cpp:137
+    const bool bcast_ok = N >= 256;
+    if ((h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
+        int rc = ensure_bcast(h);
+        if (rc) return rc;
+        BcastArgs a{};
+        a.stream = stream_dev;
+        a.row_stride = n_samples;
+        a.n_frames = n_frames;
+        a.frame_len = N;
+        a.frame_stride = N;
+        a.table = h->d_bcast_table.p;
+        a.tile_dirs = h->d_bcast_dirs.p;
+        a.n_tiles = h->bcast_tiles;
+        a.usable = usable;
+        a.n_dir = h->dir_count;
+        a.index = h->d_index.p;
+        a.geom = h->bcast_geom;
+        a.power = power_dev;
+        a.norm = norm;
+        BFLK_CUDA(h, h->d_packed.reserve(das_bcast_packed_bytes(a)));
+        a.packed = h->d_packed.p;
+        const int nblk = N <= 256 ? 1 : (N - 2 + 253) / 254;
+        if (nblk > 1) {
+            BFLK_CUDA(h, h->d_partial.reserve((size_t)n_frames * nblk * h->dir_count));
+            a.partial = h->d_partial.p;
+        }
+        int launches = 0;
+        BFLK_CUDA(h, launch_das_bcast(a, st, &launches, timing_hook, h));
+        h->launches += launches;
+        h->kernel_last = 3;
+        return BFLK_OK;
+    }
+    if (h->kernel_choice == 3)
+        return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256");
     bool tiled = false;
     if (h->kernel_choice != 1) {
         int rc = ensure_tiles(h);

@@ -31,22 +31,36 @@ struct __align__(16) TileEntry {
 };
 
 // Tiling constants shared by the table builder (tables.cu) and the kernel (das_tile.cu).
-constexpr int kTileWarps = 12;  // direction tiles (= compute warps) per CTA
 constexpr int kTileCC = 16;     // channels per pipeline stage
-// Tile tables are stored per (tile group, stage) so that one bulk copy fetches a CTA's stage:
-// entry(tile t, channel slot s) = tiles[((t / kTileWarps) * n_stage + s / kTileCC) * kTileWarps * kTileCC
-//                                       + (t % kTileWarps) * kTileCC + s % kTileCC],  n_stage = ceil(usable / kTileCC).
-inline size_t tile_table_entries(int n_tiles, int usable) {
-    const size_t groups = (n_tiles + kTileWarps - 1) / kTileWarps, stages = (usable + kTileCC - 1) / kTileCC;
-    return groups * stages * kTileWarps * kTileCC;
+// Tile tables are stored per (tile group, stage) so that one bulk copy fetches a CTA's stage; a group is
+// the `warps` direction tiles one CTA works on (one per compute warp):
+// entry(tile t, channel slot s) = tiles[((t / warps) * n_stage + s / kTileCC) * warps * kTileCC
+//                                       + (t % warps) * kTileCC + s % kTileCC],  n_stage = ceil(usable / kTileCC).
+inline size_t tile_table_entries(int n_tiles, int usable, int warps) {
+    const size_t groups = (n_tiles + warps - 1) / warps, stages = (usable + kTileCC - 1) / kTileCC;
+    return groups * stages * warps * kTileCC;
 }
 
 // Shape of the packed rows the tiled kernel stages (das_tile.cu).
 struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
     int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
+    int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
     int row_chunks = 0;  // logical chunks per packed row
     int row_bytes = 0;   // padded bytes per packed row
+};
+
+// ---- lane-broadcast kernel (das_bcast.cu) -----------------------------------------------------------------
+constexpr int kBcastCC = 8;  // channels per pipeline stage
+struct BcastEntry {
+    int32_t joff;  // byte offset of the lane's first row element (16 * (offset - smallest offset))
+    float frac;    // fractional delay
+};
+struct BcastGeometry {
+    int first_offset = 0;  // smallest offset in the LUT (history - max_delay)
+    int first_sample = 0;  // block sample of row element 0
+    int row_elems = 0;     // float4 elements per packed row
+    int row_bytes = 0;
 };
 
 template <typename T>
@@ -127,6 +141,14 @@ struct bflk_handle {
     bflk::TileGeometry tile_geom;
     bflk::DevBuf<char> d_packed;            // pair-interleaved staging rows of the current batch
 
+    // lane-broadcast kernel tables (built lazily for the current grid / mask / range)
+    bool bcast_valid = false;
+    int32_t bcast_tiles = 0;
+    bflk::BcastGeometry bcast_geom;
+    bflk::DevBuf<bflk::BcastEntry> d_bcast_table;  // [tile][stage][kBcastCC][32]
+    bflk::DevBuf<int32_t> d_bcast_dirs;            // [tile][32] local direction index or -1
+    bflk::DevBuf<int32_t> d_bcast_globals;         // [tile][32] grid direction index or -1
+
     // scratch
     bflk::DevBuf<float> d_window, d_power, d_audio, d_partial;
     bflk::DevBuf<bflk::DirTrig> d_trig;
@@ -170,7 +192,7 @@ cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d
 cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st);
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, TileEntry *d_tiles,
+                               int rows, int cols, int first, int count, int stage_off, int warps, TileEntry *d_tiles,
                                int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
@@ -218,6 +240,29 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
 int das_tile_max_span();
 TileGeometry das_tile_geometry(int history, int max_delay, int max_span);
 size_t das_tile_packed_bytes(const TileArgs &a);
+
+// ---- das_bcast.cu -----------------------------------------------------------------------------------
+struct BcastArgs {
+    const float *stream;
+    int64_t row_stride;
+    int n_frames, frame_len, frame_stride;
+    const BcastEntry *table;
+    const int32_t *tile_dirs;   // [n_tiles][32] local direction index or -1
+    int n_tiles, usable, n_dir;
+    const int32_t *index;
+    BcastGeometry geom;
+    void *packed;               // das_bcast_packed_bytes() of scratch
+    float *power, *partial;
+    float norm;
+};
+BcastGeometry das_bcast_geometry(int history, int max_delay);
+size_t das_bcast_table_entries(int n_tiles, int usable);
+size_t das_bcast_packed_bytes(const BcastArgs &a);
+cudaError_t launch_bcast_table(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
+                               const int32_t *d_tile_globals, int n_tiles, const BcastGeometry &g, BcastEntry *d_table,
+                               cudaStream_t st);
+cudaError_t launch_das_bcast(const BcastArgs &a, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
+                             void *hook_ctx = nullptr);
 
 // ---- post.cu ----------------------------------------------------------------------------------------
 cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st);

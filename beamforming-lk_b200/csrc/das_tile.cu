@@ -19,74 +19,19 @@
 //    reference's exact operation triple, so the delayed sums are bit-identical to the CPU path.
 //  * epilogue: 3-tap high-pass + squares (mimo.cpp:131-135) with neighbour samples from lane +-1,
 //    warp-shuffle reduction, one store per (block, direction).
-#include <cuda/std/cstdint>
+#include <cstdlib>
 
 #include "bflk_internal.h"
+#include "das_common.cuh"
 
 namespace bflk {
 
 namespace {
 
-constexpr int kWarps = kTileWarps;   // compute warps per CTA = direction tiles per CTA
-constexpr int kThreads = kWarps * 32;
 constexpr int kCC = kTileCC;         // channels per pipeline stage
 constexpr int kStages = 3;
 constexpr int kBlock = 256;          // output samples per block
 constexpr int kK = 8;                // sample pairs per lane
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-    u64 d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 dup2(float f) {
-    u64 d;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(f));
-    return d;
-}
-__device__ __forceinline__ float lo(u64 v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
-__device__ __forceinline__ void lds128(u64 &a, u64 &b, uint32_t addr) {
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
 
 // chunk (16 B = 2 sample pairs) c of a row lives at padded chunk c + (c >> 2)
 __host__ __device__ __forceinline__ int padded_chunk(int c) { return c + (c >> 2); }
@@ -165,29 +110,49 @@ __device__ __forceinline__ void load_window(u64 (&w)[2 * NCH], uint32_t addr) {
 // acc[k] += fma(f, d[D + k], w[D + k + 1]) for the 8 sample pairs of this lane (delay.cpp:24)
 template <int NCH, int D>
 __device__ __forceinline__ void accumulate(u64 (&acc)[kK], const u64 (&w)[2 * NCH], const u64 (&d)[2 * NCH - 1], u64 ff) {
+    // software-pipelined by hand: the FADD2 of sample k issues four packed instructions after its FFMA2,
+    // so a single warp never waits on the FMA latency
+    u64 t[kK];
 #pragma unroll
-    for (int k = 0; k < kK; k++) acc[k] = add2(acc[k], fma2(ff, d[D + k], w[D + k + 1]));
+    for (int k = 0; k < 4; k++) t[k] = fma2(ff, d[D + k], w[D + k + 1]);
+#pragma unroll
+    for (int k = 0; k < kK; k++) {
+        acc[k] = add2(acc[k], t[k]);
+        if (k + 4 < kK) t[k + 4] = fma2(ff, d[D + k + 4], w[D + k + 5]);
+    }
 }
 
-template <int NCH>
-__device__ __forceinline__ void accumulate_dyn(int delta, u64 (&acc)[kK], const u64 (&w)[2 * NCH], const u64 (&d)[2 * NCH - 1],
-                                               float f) {
-    const u64 ff = dup2(f);
+// Warp-uniform dispatch on delta as a binary tree over its bits: predicated direct branches instead of a
+// jump-table load + indirect branch (the table load and BRX resolve dominated the first version's stalls).
+// The four bit predicates are formed together before the first branch so the branches do not wait on them.
+template <int NCH, int D0, int BITS>
+__device__ __forceinline__ void accumulate_tree(const bool (&bits)[4], u64 (&acc)[kK], const u64 (&w)[2 * NCH],
+                                                const u64 (&d)[2 * NCH - 1], u64 ff) {
     constexpr int kMax = 2 * NCH - 9;  // largest delta whose window still fits the loaded chunks
-    switch (delta) {
-#define BFLK_CASE(D) \
-    case D:          \
-        if constexpr (D <= kMax) accumulate<NCH, (D <= kMax ? D : 0)>(acc, w, d, ff); \
-        break;
-        BFLK_CASE(0) BFLK_CASE(1) BFLK_CASE(2) BFLK_CASE(3) BFLK_CASE(4) BFLK_CASE(5) BFLK_CASE(6) BFLK_CASE(7)
-        BFLK_CASE(8) BFLK_CASE(9) BFLK_CASE(10) BFLK_CASE(11)
-#undef BFLK_CASE
-        default: break;
+    if constexpr (D0 > kMax) {
+        return;
+    } else if constexpr (BITS == 0) {
+        accumulate<NCH, D0>(acc, w, d, ff);
+    } else {
+        constexpr int bit = 1 << (BITS - 1);
+        if constexpr (D0 + bit > kMax) {
+            accumulate_tree<NCH, D0, BITS - 1>(bits, acc, w, d, ff);
+        } else {
+            if (bits[BITS - 1]) accumulate_tree<NCH, D0 + bit, BITS - 1>(bits, acc, w, d, ff);
+            else accumulate_tree<NCH, D0, BITS - 1>(bits, acc, w, d, ff);
+        }
     }
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(kThreads, 1) das_tile_kernel(KernelArgs a) {
+__device__ __forceinline__ void accumulate_dyn(uint32_t delta, u64 (&acc)[kK], const u64 (&w)[2 * NCH],
+                                               const u64 (&d)[2 * NCH - 1], float f) {
+    const bool bits[4] = {(delta & 1u) != 0, (delta & 2u) != 0, (delta & 4u) != 0, (delta & 8u) != 0};
+    accumulate_tree<NCH, 0, 4>(bits, acc, w, d, dup2(f));
+}
+
+template <int NCH, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * 32 } then barriers
     const int stage_rows = kCC * a.row_bytes;
@@ -244,26 +209,33 @@ __global__ void __launch_bounds__(kThreads, 1) das_tile_kernel(KernelArgs a) {
         const uint32_t rows_s = smem + buf * stage_bytes;
         const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * (int)sizeof(TileEntry);
         const int nc = min(kCC, a.usable - st * kCC);
-        for (int c = 0; active && c < nc; c++) {
-            uint32_t e0, e1, e2, e3;
-            float f0, f1, f2, f3;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(tiles_s + 32 * c));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(tiles_s + 32 * c + 16));
-            const uint32_t addr = rows_s + c * a.row_bytes + e0 + lane_off;
-            u64 w[2 * NCH];
-            switch (e1 >> 24) {
-                case 0: load_window<NCH, 0>(w, addr); break;
-                case 1: load_window<NCH, 1>(w, addr); break;
-                case 2: load_window<NCH, 2>(w, addr); break;
-                default: load_window<NCH, 3>(w, addr); break;
-            }
-            u64 d[2 * NCH - 1];
+        if (active) {
+            uint32_t e0, e1, n0, n1;
+            float f0, f1, f2, f3, g0, g1, g2, g3;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(tiles_s));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(tiles_s + 16));
+            for (int c = 0; c < nc; c++) {
+                // the next channel's table entry is fetched one iteration ahead (its latency hides behind this channel)
+                const uint32_t nt = tiles_s + 32 * min(c + 1, nc - 1);
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n0), "=r"(n1) : "r"(nt));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3) : "r"(nt + 16));
+                const uint32_t addr = rows_s + c * a.row_bytes + e0 + lane_off;
+                u64 w[2 * NCH];
+                switch (e1 >> 24) {
+                    case 0: load_window<NCH, 0>(w, addr); break;
+                    case 1: load_window<NCH, 1>(w, addr); break;
+                    case 2: load_window<NCH, 2>(w, addr); break;
+                    default: load_window<NCH, 3>(w, addr); break;
+                }
+                u64 d[2 * NCH - 1];
 #pragma unroll
-            for (int j = 0; j < 2 * NCH - 1; j++) d[j] = sub2(w[j], w[j + 1]);  // s[i] - s[i+1], once per window
-            accumulate_dyn<NCH>(e1 & 63, acc[0], w, d, f0);
-            accumulate_dyn<NCH>((e1 >> 6) & 63, acc[1], w, d, f1);
-            accumulate_dyn<NCH>((e1 >> 12) & 63, acc[2], w, d, f2);
-            accumulate_dyn<NCH>((e1 >> 18) & 63, acc[3], w, d, f3);
+                for (int j = 0; j < 2 * NCH - 1; j++) d[j] = sub2(w[j], w[j + 1]);  // s[i] - s[i+1], once per window
+                accumulate_dyn<NCH>(e1 & 63, acc[0], w, d, f0);
+                accumulate_dyn<NCH>((e1 >> 6) & 63, acc[1], w, d, f1);
+                accumulate_dyn<NCH>((e1 >> 12) & 63, acc[2], w, d, f2);
+                accumulate_dyn<NCH>((e1 >> 18) & 63, acc[3], w, d, f3);
+                e0 = n0; e1 = n1; f0 = g0; f1 = g1; f2 = g2; f3 = g3;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 8 * (kStages + buf));
@@ -332,17 +304,22 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span) {
     TileGeometry g;
     g.stage_off = (history - max_delay) & ~1;
     g.nch = max_span <= 3 ? 6 : (max_span <= 7 ? 8 : 10);
+    g.warps = 12;  // measured on B200: 12 warps (3 per scheduler) beat 10 or 8 with more registers each
+    if (const char *env = getenv("BFLK_TILE_WARPS")) {  // tuning knob: 8, 10 or 12 compute warps per CTA
+        const int v = atoi(env);
+        if (v == 8 || v == 10 || v == 12) g.warps = v;
+    }
     // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
     g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
     g.row_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
     return g;
 }
 
-template <int NCH>
+template <int NCH, int WARPS>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    das_tile_kernel<NCH><<<grid, kThreads, smem, st>>>(k);
+    das_tile_kernel<NCH, WARPS><<<grid, WARPS * 32, smem, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -373,6 +350,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.row_chunks = a.geom.row_chunks;
     p.row_bytes = a.geom.row_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
+    const int kWarps = a.geom.warps;
     const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * sizeof(TileEntry)) + 2 * kStages * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 
@@ -407,9 +385,16 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         dim3 grid((a.n_tiles + kWarps - 1) / kWarps, np);
         if (hook) hook(hook_ctx, 0, true, st);
         switch (a.geom.nch) {
-            case 6: e = launch_main<6>(ks, grid, smem, st); break;
-            case 8: e = launch_main<8>(ks, grid, smem, st); break;
-            default: e = launch_main<10>(ks, grid, smem, st); break;
+#define BFLK_LAUNCH(NCH)                                                              \
+    switch (a.geom.warps) {                                                            \
+        case 8: e = launch_main<NCH, 8>(ks, grid, smem, st); break;                    \
+        case 10: e = launch_main<NCH, 10>(ks, grid, smem, st); break;                  \
+        default: e = launch_main<NCH, 12>(ks, grid, smem, st); break;                  \
+    }
+            case 6: BFLK_LAUNCH(6) break;
+            case 8: BFLK_LAUNCH(8) break;
+            default: BFLK_LAUNCH(10) break;
+#undef BFLK_LAUNCH
         }
         if (hook) hook(hook_ctx, 0, false, st);
         if (e != cudaSuccess) return e;

@@ -90,7 +90,7 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // touches and directions outside the range get tile_dirs = -1 (computed but not stored).
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
-                                   int count, int stage_off, TileEntry *__restrict__ tiles,
+                                   int count, int stage_off, int warps, TileEntry *__restrict__ tiles,
                                    int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
                                    int32_t *__restrict__ maxspan) {
     const int t = blockIdx.x;
@@ -139,8 +139,8 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
         e.deltas = packed;
         e.span = span;
         const int n_stage = (usable + kTileCC - 1) / kTileCC;
-        tiles[((size_t)(t / kTileWarps) * n_stage + s / kTileCC) * (kTileWarps * kTileCC) + (t % kTileWarps) * kTileCC +
-              s % kTileCC] = e;
+        if (tiles)
+            tiles[((size_t)(t / warps) * n_stage + s / kTileCC) * (warps * kTileCC) + (t % warps) * kTileCC + s % kTileCC] = e;
         span_max = max(span_max, span);
     }
     for (int o = 16; o > 0; o >>= 1) span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o));
@@ -148,12 +148,12 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 }
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, TileEntry *d_tiles,
+                               int rows, int cols, int first, int count, int stage_off, int warps, TileEntry *d_tiles,
                                int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
     build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
-                                                d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+                                                warps, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

@@ -101,9 +101,10 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
 /* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream);
-/* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel. */
+/* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel,
+ * 3 = lane-broadcast kernel. */
 int bflk_set_kernel(bflk_handle *h, int32_t which);
-/* Which kernel the last power-map call used (1 generic, 2 tiled; 0 = none yet), the largest offset spread
+/* Which kernel the last power-map call used (1 generic, 2 tiled, 3 lane-broadcast; 0 = none yet), the largest offset spread
  * inside a 2x2 direction tile for the current grid, and the window chunks of the tiled variant in use. */
 int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */

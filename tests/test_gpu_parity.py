@@ -72,7 +72,7 @@ def test_dynamic_steer_tables_bit_exact(bf, oracle, golden):
 
 
 # ---- the golden snapshot through every entry point ----------------------------------------------------------
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_snapshot_power_map(bf, golden, kernel):
     g = golden["snapshot"]
     w = bf.MIMOWorker(cases.origins(1, 1), 16, 16, 180.0)
@@ -121,7 +121,7 @@ def _synth_window(bf, c, n_samples=None, sigma=1e-3):
     return synth.make_stream(xyz, n_samples or c["W"], sigma=sigma)
 
 
-@pytest.mark.parametrize("name,kernel", [("cfg1", 2), ("cfg2", 2), ("cfg3", 2), ("cfg3", 1)])
+@pytest.mark.parametrize("name,kernel", [("cfg1", 2), ("cfg2", 2), ("cfg3", 2), ("cfg3", 1), ("cfg1", 3), ("cfg2", 3), ("cfg3", 3)])
 def test_config_power_map_vs_oracle(bf, oracle, name, kernel):
     c = cases.CONFIGS[name]
     w = make(bf, c)
@@ -160,7 +160,12 @@ def test_cfg5_subset_and_properties(bf, oracle):
     window = _synth_window(bf, c)
     D = c["rows"] * c["cols"]
     p = w.update(window)
-    assert w.kernel_info()[0] == 2               # automatic choice = the register-tiled kernel
+    assert w.kernel_info()[0] in (2, 3)          # automatic choice = one of the two fast kernels
+    for k in (2, 3):                             # both fast kernels agree with each other and the oracle
+        w.set_kernel(k)
+        pk = w.update(window)
+        assert w.kernel_info()[0] == k and rel_err(pk, p) <= POWER_RTOL
+    w.set_kernel(0)
     assert p.shape == (D,) and np.all(np.isfinite(p)) and p.min() > 0
     off, fr = w.tables()
     sel = np.r_[0:4, 128 * 256 + 126:128 * 256 + 130, D - 3:D, np.arange(17, D, 4099)]
@@ -195,7 +200,7 @@ def test_cfg4_miso_vs_oracle(bf, oracle):
 
 
 # ---- batching, sharding, masks, edge cases -----------------------------------------------------------------------
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_batch_equals_single_frames(bf, oracle, kernel):
     c = cases.CONFIGS["cfg3"]
     B = 5
@@ -212,7 +217,7 @@ def test_batch_equals_single_frames(bf, oracle, kernel):
     assert rel_err(pb[3], po) <= POWER_RTOL
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
     c = cases.CONFIGS["cfg2"]
     w = make(bf, c)
