@@ -511,8 +511,21 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const int N = h->cfg.frame_len, C = h->cfg.n_channels, usable = (int)h->index.size();
     const float norm = static_cast<float>(N * usable);  // power /= float(N_SAMPLES * count), mimo.cpp:137
+    // automatic choice: register-tiled kernel when the grid tiles (2x2 direction tiles with small offset
+    // spread), else the lane-broadcast kernel (any direction list), else the generic kernel (any frame length)
+    bool tiled = false;
+    if (h->kernel_choice == 0 || h->kernel_choice == 2) {
+        int rc = ensure_tiles(h);
+        if (rc) return rc;
+        tiled = h->tiles_usable && !(n_samples & 1);  // packed rows are gathered with 8-byte loads
+        if (h->kernel_choice == 2 && !tiled)
+            return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
+                           h->tile_smax, das_tile_max_span());
+    }
     const bool bcast_ok = N >= 256;
-    if ((h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
+    if (h->kernel_choice == 3 && !bcast_ok)
+        return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256");
+    if (!tiled && (h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
         int rc = ensure_bcast(h);
         if (rc) return rc;
         BcastArgs a{};
@@ -542,18 +555,6 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
         h->launches += launches;
         h->kernel_last = 3;
         return BFLK_OK;
-    }
-    if (h->kernel_choice == 3)
-        return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256");
-    bool tiled = false;
-    if (h->kernel_choice != 1) {
-        int rc = ensure_tiles(h);
-        if (rc) return rc;
-        tiled = h->tiles_usable;
-        if (tiled && (n_samples & 1)) tiled = false;  // packed rows are gathered with 8-byte loads
-        if (h->kernel_choice == 2 && !tiled)
-            return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
-                           h->tile_smax, das_tile_max_span());
     }
     if (tiled) {
         TileArgs a{};

@@ -151,6 +151,8 @@ __device__ __forceinline__ void accumulate_dyn(uint32_t delta, u64 (&acc)[kK], c
     accumulate_tree<NCH, 0, 4>(bits, acc, w, d, dup2(f));
 }
 
+#include "das_tile_asm.inc"
+
 template <int NCH, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
             float f0, f1, f2, f3, g0, g1, g2, g3;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(tiles_s));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(tiles_s + 16));
+#pragma unroll 1
             for (int c = 0; c < nc; c++) {
                 // the next channel's table entry is fetched one iteration ahead (its latency hides behind this channel)
                 const uint32_t nt = tiles_s + 32 * min(c + 1, nc - 1);
@@ -230,10 +233,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
                 u64 d[2 * NCH - 1];
 #pragma unroll
                 for (int j = 0; j < 2 * NCH - 1; j++) d[j] = sub2(w[j], w[j + 1]);  // s[i] - s[i+1], once per window
+#ifdef BFLK_TILE_CPP_DISPATCH
                 accumulate_dyn<NCH>(e1 & 63, acc[0], w, d, f0);
                 accumulate_dyn<NCH>((e1 >> 6) & 63, acc[1], w, d, f1);
                 accumulate_dyn<NCH>((e1 >> 12) & 63, acc[2], w, d, f2);
                 accumulate_dyn<NCH>((e1 >> 18) & 63, acc[3], w, d, f3);
+#else
+                tile_channel_asm(acc, w, d, f0, f1, f2, f3, e1);  // hand-scheduled PTX, tools/gen_tile_asm.py
+#endif
                 e0 = n0; e1 = n1; f0 = g0; f1 = g1; f2 = g2; f3 = g3;
             }
         }

@@ -85,6 +85,7 @@ class ClockSampler:
         self.index, self.samples, self.reasons, self.stop = index, [], set(), threading.Event()
         self.max_mhz = None
         self.thread = None
+        self.t0 = self.t1 = None     # the timed region; only samples inside it are reported
 
     def _run(self):
         try:
@@ -100,15 +101,13 @@ class ClockSampler:
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
             while not self.stop.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.02)
+                self.samples.append((time.perf_counter(), mhz, r, names))
+                time.sleep(0.005)
         except Exception as e:  # NVML unavailable: report that rather than fail the bench
             self.reasons.add(f"nvml_error:{type(e).__name__}")
 
@@ -121,9 +120,20 @@ class ClockSampler:
         self.stop.set()
         self.thread.join(timeout=2)
 
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
     def summary(self):
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or 1e30)]
+        for _, _, r, names in inside:
+            for bit, nm in names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        return {"sm_mhz": statistics.median([s[1] for s in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(inside), "reasons": sorted(self.reasons)}
 
 
 def make_input(c, T):
@@ -201,6 +211,7 @@ def run_ours(args, c, name):
     import torch
     import torch.distributed as dist
     import bflk
+    from bflk import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,18 +229,19 @@ def run_ours(args, c, name):
     C, D, N = 64 * c["nx"] * c["ny"], c["rows"] * c["cols"], c["N"]
     cfg = workload(c, name, B)
     T = cfg["samples_per_channel"]
-    if D % world:
-        raise SystemExit("grid does not divide across ranks")
-    per = D // world
+    first, count = shard.direction_shard(D, world, rank)
+    per = shard.padded_count(D, world)
 
     w = bflk.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"], device=local,
                         frame_len=N, history=c["H"], window_len=c["W"])
     w.set_kernel(args.kernel)
-    w.set_direction_range(rank * per, per)
+    w.set_direction_range(first, count)
 
     host_in = torch.from_numpy(make_input(c, T)).pin_memory()
     stream_dev = host_in.to(dev, non_blocking=True)
-    local_pow = torch.empty((B, per), dtype=torch.float32, device=dev)
+    local_pow = torch.zeros((B, per), dtype=torch.float32, device=dev)
+    local_view = local_pow if count == per else None      # ragged shard: the kernel writes a [B][count] buffer
+    local_tight = local_pow if count == per else torch.empty((B, count), dtype=torch.float32, device=dev)
     gathered = torch.empty((world, B, per), dtype=torch.float32, device=dev) if world > 1 else None
     host_out = torch.empty((B, D), dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
@@ -240,9 +252,11 @@ def run_ours(args, c, name):
     assert cs != 0
 
     def step():
-        w.power_map_batch_dev(stream_dev.data_ptr(), T, B, local_pow.data_ptr(), cs)
+        w.power_map_batch_dev(stream_dev.data_ptr(), T, B, local_tight.data_ptr(), cs)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, local_pow)
+            if local_view is None:
+                local_pow[:, :count].copy_(local_tight)
+            shard.gather_maps(local_pow, D, out=gathered)
 
     def barrier():
         if world > 1:
@@ -265,14 +279,16 @@ def run_ours(args, c, name):
         return float(ms.item())
 
     # ---- device-resident throughput, dominant-kernel time and clocks over the timed region ----
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    w.enable_timing(True)
-    w.kernel_time_ms()
-    l0 = w.launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:       # NVML start-up overlaps the warm-up; samples are filtered to the timed region
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        w.enable_timing(True)
+        w.kernel_time_ms()
+        l0 = w.launch_count()
+        clk.begin()
         ms = timed(step, args.steps, 0)
+        clk.end()
     launches = w.launch_count() - l0
     das_ms, das_n, pack_ms, pack_n = w.kernel_time_ms()
     w.enable_timing(False)
@@ -291,7 +307,7 @@ def run_ours(args, c, name):
             def e2e_step():
                 stream_dev.copy_(host_in, non_blocking=True)
                 step()
-                host_out.view(B, world, per).copy_(full.permute(1, 0, 2), non_blocking=True)
+                host_out.copy_(shard.assemble(full, D), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         e2e_steps = max(3, args.steps // 3)
         if world == 1:
@@ -315,10 +331,10 @@ def run_ours(args, c, name):
         max_mhz = pk.get("sm_max_mhz") or clocks["sm_max_mhz"] or 1965.0
         peak_tf = sm_count * FP32_LANES_PER_SM * 2 * max_mhz * 1e6 / 1e12
         # algorithmic FLOPs one das launch performs on this rank: B maps x per directions
-        fl = flops_per_map(C, per, N) * B
+        fl = flops_per_map(C, count, N) * B
         das_avg_s = das_ms / 1e3 / max(1, das_n)
         achieved_tf = fl / das_avg_s / 1e12 if das_n else None
-        alg_bytes = 4 * C * T + 4 * B * per
+        alg_bytes = 4 * C * T + 4 * B * count
         roof = {"bound": "fp32", "kernel": {1: "das_generic", 2: "das_tile", 3: "das_bcast"}.get(kinfo[0], "?"), "achieved": achieved_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if achieved_tf else None,
                 "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz {max_mhz:.0f} ({pk_kind} MEASURED_PEAKS.json clock)",
@@ -328,7 +344,7 @@ def run_ours(args, c, name):
         roof_hbm = {"bound": "hbm", "achieved": alg_bytes / das_avg_s / 1e9 if das_n else None, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
                     "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
-        cfg.update(parallelism=f"direction-sharded x{world}" if world > 1 else "single GPU", directions_per_gpu=per,
+        cfg.update(parallelism=f"direction-sharded x{world}" if world > 1 else "single GPU", directions_per_gpu=count,
                    kernel=roof["kernel"], tile_span=kinfo[1], window_chunks=kinfo[2])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
