@@ -224,11 +224,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3) : "r"(nt + 16));
                 const uint32_t addr = rows_s + c * a.row_bytes + e0 + lane_off;
                 u64 w[2 * NCH];
-                switch (e1 >> 24) {
-                    case 0: load_window<NCH, 0>(w, addr); break;
-                    case 1: load_window<NCH, 1>(w, addr); break;
-                    case 2: load_window<NCH, 2>(w, addr); break;
-                    default: load_window<NCH, 3>(w, addr); break;
+                {
+                    // chunk m of the window sits at padded chunk m + ((r + m) >> 2), r = (first chunk) & 3: the pad
+                    // correction is 16 * (m >> 2) plus 16 more when r + (m & 3) >= 4 -> one of two base registers
+                    const uint32_t r = e1 >> 24, hi = addr + 16;
+                    const uint32_t base[4] = {addr, r >= 3 ? hi : addr, r >= 2 ? hi : addr, r >= 1 ? hi : addr};
+#pragma unroll
+                    for (int m = 0; m < NCH; m++) lds128(w[2 * m], w[2 * m + 1], base[m & 3] + 16 * (m + (m >> 2)));
                 }
                 u64 d[2 * NCH - 1];
 #pragma unroll
