@@ -14,23 +14,30 @@ usage: python tools/gen_tile_asm.py > beamforming-lk_b200/csrc/das_tile_asm.inc
 K = 8
 
 
+import os
+VOTE = os.environ.get('BFLK_GEN_VOTE', '0') == '1'   # measured slower on B200 (extra VOTE + BRA.DIV per direction)
+BRX = os.environ.get('BFLK_GEN_BRX', '0') == '1'     # indexed jump instead of the bit tree
+DEPTH = 4   # FFMA2 -> FADD2 software-pipeline depth (temporaries); set per variant in gen()
+
+
 def body(r, D, lines, ind="    "):
-    """acc[r][k] = acc[r][k] + fma(ff, d[D+k], w[D+k+1]), k = 0..7 (delay.cpp:24), pipelined 4 deep."""
+    """acc[r][k] = acc[r][k] + fma(ff, d[D+k], w[D+k+1]), k = 0..7 (delay.cpp:24), pipelined DEPTH deep."""
     def fma(t, k):
         lines.append(f"{ind}fma.rn.f32x2 t{t}, ff, %{DOP(D + k)}, %{WOP(D + k + 1)};")
 
     def add(k, t):
         lines.append(f"{ind}add.rn.f32x2 %{AOP(r, k)}, %{AOP(r, k)}, t{t};")
-    for k in range(4):
+    for k in range(DEPTH):
         fma(k, k)
     for k in range(K):
-        add(k, k % 4)
-        if k + 4 < K:
-            fma(k % 4, k + 4)
+        add(k, k % DEPTH)
+        if k + DEPTH < K:
+            fma(k % DEPTH, k + DEPTH)
 
 
 def gen(nch):
-    global AOP, WOP, DOP
+    global AOP, WOP, DOP, DEPTH
+    DEPTH = 8 if nch <= 8 else 4
     nw = 2 * nch           # w[0 .. 2nch-1]; w[0] is never an FMA operand
     nd = 2 * nch - 1       # d[0 .. 2nch-2]
     kmax = 2 * nch - 9
@@ -47,13 +54,17 @@ def gen(nch):
     sets = ["pa", "pb"] if dbl else ["pa", "pa"]
     L.append(f"    .reg .pred pa<{nbits}>, pb<{nbits}>;")
     L.append("    .reg .b32 x;")
-    L.append("    .reg .b64 ff, t<4>;")
+    L.append(f"    .reg .b64 ff, t<{DEPTH}>;")
 
     def preds(r, ps):
         L.append(f"    // predicates of direction {r}: bits of delta = (e1 >> {6 * r}) & 63")
         for b in range(nbits):
             L.append(f"    and.b32 x, %{EOP}, {1 << (6 * r + b)};")
             L.append(f"    setp.ne.b32 {ps}{b}, x, 0;")
+            if VOTE:
+                # the offsets are warp-uniform by construction; a vote makes that visible to ptxas, which then
+                # uses uniform predicates + BRA.U and drops the BSSY / BSYNC reconvergence bookkeeping
+                L.append(f"    vote.sync.any.pred {ps}{b}, {ps}{b}, 0xffffffff;")
 
     preds(0, sets[0])
     for r in range(4):
@@ -66,6 +77,7 @@ def gen(nch):
             preds(r, ps)
         L.append(f"    // ---- direction {r}")
         L.append(f"    mov.b64 ff, {{%{FOP(r)}, %{FOP(r)}}};")
+        tree_start = len(L)
 
         def tree(d0, bit):
             # dispatches among deltas d0 .. d0 + 2^(bit+1) - 1 (clipped to kmax)
@@ -81,7 +93,20 @@ def gen(nch):
             tree(d0, bit - 1)
             L.append(f"T{r}_{hi}_{bit}:")
             tree(hi, bit - 1)
-        tree(0, nbits - 1)
+        if BRX:
+            # undo the tree: one indexed jump (LDC + BRX) to the case body
+            del L[tree_start:]
+            labels = ", ".join(f"C{r}_{dd}" for dd in range(kmax + 1))
+            L.append(f"    bfe.u32 x, %{EOP}, {6 * r}, 6;")
+            L.append(f"    min.u32 x, x, {kmax};")
+            L.append(f"TS{r}: .branchtargets {labels};")
+            L.append(f"    brx.idx.uni x, TS{r};")
+            for dd in range(kmax + 1):
+                L.append(f"C{r}_{dd}:")
+                body(r, dd, L)
+                L.append(f"    bra.uni J{r};")
+        else:
+            tree(0, nbits - 1)
         L.append(f"J{r}:")
     L.append("}")
     asm = "\n".join(f'        "{ln}\\n"' for ln in L)
