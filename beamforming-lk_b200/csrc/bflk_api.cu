@@ -77,6 +77,8 @@ int bflk_destroy(bflk_handle *h) {
         cudaStreamSynchronize(h->stream);
         cudaStreamDestroy(h->stream);
     }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
@@ -499,8 +501,9 @@ static int ensure_bcast(bflk_handle *h) {
     return BFLK_OK;
 }
 
-int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
-                             float *power_dev, void *cuda_stream) {
+// stream_dev: first sample of frame 0; rows are row_stride floats apart and hold row_len valid samples
+static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
+                         float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
     if (!stream_dev || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
@@ -517,7 +520,7 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     if (h->kernel_choice == 0 || h->kernel_choice == 2) {
         int rc = ensure_tiles(h);
         if (rc) return rc;
-        tiled = h->tiles_usable && !(n_samples & 1);  // packed rows are gathered with 8-byte loads
+        tiled = h->tiles_usable && !(row_stride & 1) && !((uintptr_t)stream_dev & 7);  // packed rows: 8-byte loads
         if (h->kernel_choice == 2 && !tiled)
             return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
                            h->tile_smax, das_tile_max_span());
@@ -530,7 +533,8 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
         if (rc) return rc;
         BcastArgs a{};
         a.stream = stream_dev;
-        a.row_stride = n_samples;
+        a.row_stride = row_stride;
+        a.row_len = n_samples;
         a.n_frames = n_frames;
         a.frame_len = N;
         a.frame_stride = N;
@@ -559,7 +563,8 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     if (tiled) {
         TileArgs a{};
         a.stream = stream_dev;
-        a.row_stride = n_samples;
+        a.row_stride = row_stride;
+        a.row_len = n_samples;
         a.n_frames = n_frames;
         a.frame_len = N;
         a.frame_stride = N;
@@ -586,7 +591,7 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     } else {
         GenericArgs a{};
         a.stream = stream_dev;
-        a.row_stride = n_samples;
+        a.row_stride = row_stride;
         a.n_frames = n_frames;
         a.frame_len = N;
         a.frame_stride = N;
@@ -608,18 +613,53 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
     return BFLK_OK;
 }
 
+int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                             float *power_dev, void *cuda_stream) {
+    return power_map_dev(h, stream_dev, n_samples, n_samples, n_frames, power_dev, cuda_stream);
+}
+
 int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
     if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    if (n_samples < min_stream_samples(h, n_frames))
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
+                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
-    const size_t n_in = (size_t)h->cfg.n_channels * n_samples, n_out = (size_t)n_frames * h->dir_count;
+    const int C = h->cfg.n_channels, N = h->cfg.frame_len;
+    const size_t n_in = (size_t)C * n_samples, n_out = (size_t)n_frames * h->dir_count;
     BFLK_CUDA(h, h->d_window.reserve(n_in));
     BFLK_CUDA(h, h->d_power.reserve(n_out));
-    BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, stream, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    int rc = bflk_power_map_batch_dev(h, h->d_window.p, n_samples, n_frames, h->d_power.p, h->stream);
-    if (rc) return rc;
-    BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    // Chunks of frames: the H2D copy of chunk k+1 (copy_stream) overlaps the kernels of chunk k (stream).
+    // A chunk is ~32 MiB of new samples so PCIe and the SMs both stay busy; small batches are one chunk.
+    const int64_t tail = min_stream_samples(h, 1) - N;  // samples a frame needs beyond its own N
+    int chunk_frames = (int)std::max<int64_t>(1, (32ll << 20) / ((int64_t)C * N * sizeof(float)));
+    if (chunk_frames * 2 > n_frames) chunk_frames = n_frames;
+    const int n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    if (!h->copy_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    while ((int)h->chunk_events.size() < n_chunks) {
+        cudaEvent_t e;
+        BFLK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunk_events.push_back(e);
+    }
+    int64_t copied = 0;  // samples per row already on the device
+    for (int k = 0; k < n_chunks; k++) {
+        const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
+        const int64_t need = std::min<int64_t>(n_samples, k == n_chunks - 1 ? n_samples : (int64_t)(f0 + nf) * N + tail);
+        if (need > copied) {
+            BFLK_CUDA(h, cudaMemcpy2DAsync(h->d_window.p + copied, n_samples * sizeof(float), stream + copied,
+                                           n_samples * sizeof(float), (need - copied) * sizeof(float), C,
+                                           cudaMemcpyHostToDevice, h->copy_stream));
+            copied = need;
+        }
+        BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
+        BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
+        float *pk = h->d_power.p + (size_t)f0 * h->dir_count;
+        int rc = power_map_dev(h, h->d_window.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        if (rc) return rc;
+        BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
+                                     cudaMemcpyDeviceToHost, h->stream));
+    }
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     return BFLK_OK;
 }

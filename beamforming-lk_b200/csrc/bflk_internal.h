@@ -158,6 +158,9 @@ struct bflk_handle {
     bflk::PinBuf<float> p_in, p_out;
     bflk::PinBuf<bflk::DirTrig> p_trig;
     bflk::PinBuf<int32_t> p_misc;
+    // host-buffer batches are cut into chunks: copies on copy_stream overlap compute on stream
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
 
     // optional kernel timing (bflk_enable_timing): event pairs recorded on the launching stream
     bool timing = false;
@@ -218,6 +221,7 @@ cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st);
 struct TileArgs {
     const float *stream;
     int64_t row_stride;
+    int64_t row_len;             // valid samples per row from `stream` (chunked host batches pass row_len < row_stride)
     int n_frames;
     int frame_len;
     int frame_stride;
@@ -244,7 +248,7 @@ size_t das_tile_packed_bytes(const TileArgs &a);
 // ---- das_bcast.cu -----------------------------------------------------------------------------------
 struct BcastArgs {
     const float *stream;
-    int64_t row_stride;
+    int64_t row_stride, row_len;
     int n_frames, frame_len, frame_stride;
     const BcastEntry *table;
     const int32_t *tile_dirs;   // [n_tiles][32] local direction index or -1

@@ -34,7 +34,7 @@ constexpr int kBlock = 256;
 
 struct PackArgs {
     const float *stream;
-    int64_t row_stride;
+    int64_t row_stride, row_len;
     int frame_len, frame_stride, nblk, n_items, pair0;
     const int32_t *index;
     int usable;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) bcast_pack_kernel(PackArgs a) {
     const long long tA = item_first_sample(itemA, a.nblk, a.frame_len, a.frame_stride) + a.first_sample + j;
     const long long tB = item_first_sample(itemB, a.nblk, a.frame_len, a.frame_stride) + a.first_sample + j;
     const float *row = a.stream + (size_t)a.index[s] * a.row_stride;
-    auto at = [&](long long t) { return (t >= 0 && t < a.row_stride) ? __ldg(row + t) : 0.0f; };
+    auto at = [&](long long t) { return (t >= 0 && t < a.row_len) ? __ldg(row + t) : 0.0f; };
     const float a1 = at(tA), a0 = at(tA - 1), b1 = at(tB), b0 = at(tB - 1);
     // current - next, rounded once exactly like _mm256_sub_ps(current_vec, next_vec) in delay.cpp:24
     a.packed[((size_t)pair * a.usable + s) * a.row_elems + j] = make_float4(a1, b1, __fsub_rn(a0, a1), __fsub_rn(b0, b1));
@@ -251,6 +251,7 @@ cudaError_t launch_das_bcast(const BcastArgs &a, cudaStream_t st, int *launches,
     PackArgs p{};
     p.stream = a.stream;
     p.row_stride = a.row_stride;
+    p.row_len = a.row_len;
     p.frame_len = a.frame_len;
     p.frame_stride = a.frame_stride;
     p.nblk = nblk;

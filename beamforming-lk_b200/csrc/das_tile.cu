@@ -47,6 +47,7 @@ static_assert(sizeof(TileEntry) == 32, "TileEntry is two 16-byte loads");
 struct PackArgs {
     const float *stream;
     int64_t row_stride;   // T
+    int64_t row_len;      // valid samples per row from the stream pointer (<= row_stride)
     int n_frames, frame_len, frame_stride;
     int blocks_per_frame;
     int n_items;          // n_frames * blocks_per_frame
@@ -74,10 +75,10 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     const int64_t tB = item_start(itemB, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch;
     const float *row = a.stream + (size_t)a.index[s] * a.row_stride;
     float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
-    if (tA + 1 < a.row_stride) A = *reinterpret_cast<const float2 *>(row + tA);
-    else if (tA < a.row_stride) A.x = row[tA];
-    if (tB + 1 < a.row_stride) B = *reinterpret_cast<const float2 *>(row + tB);
-    else if (tB < a.row_stride) B.x = row[tB];
+    if (tA + 1 < a.row_len) A = *reinterpret_cast<const float2 *>(row + tA);
+    else if (tA < a.row_len) A.x = row[tA];
+    if (tB + 1 < a.row_len) B = *reinterpret_cast<const float2 *>(row + tB);
+    else if (tB < a.row_len) B.x = row[tB];
     char *dst = reinterpret_cast<char *>(a.packed) + ((size_t)pair * a.usable + s) * a.row_bytes + 16 * padded_chunk(ch);
     *reinterpret_cast<float4 *>(dst) = make_float4(A.x, B.x, A.y, B.y);
 }
@@ -348,6 +349,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     PackArgs p{};
     p.stream = a.stream;
     p.row_stride = a.row_stride;
+    p.row_len = a.row_len;
     p.n_frames = a.n_frames;
     p.frame_len = a.frame_len;
     p.frame_stride = a.frame_stride;

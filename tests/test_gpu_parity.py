@@ -240,6 +240,21 @@ def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
     assert rel_err(p1, oracle.mimo_update(window, off, fr, index=np.array([17], np.int32))) <= POWER_RTOL
 
 
+def test_chunked_host_batch_equals_small_batches(bf):
+    """Host-buffer batches above ~64 MiB are copied and computed in overlapping chunks: same bits as separate calls."""
+    from bflk import synth
+    w = bf.MIMOWorker(cases.origins(1, 1), 8, 8, 180.0)
+    B = 1100                                               # 64 channels: 512 frames per 32 MiB chunk -> 3 chunks
+    base = synth.make_stream(synth.tile_geometry(cases.origins(1, 1)), 40 * 256 + 1024)
+    stream = np.ascontiguousarray(np.tile(base[:, :40 * 256], (1, B // 40 + 2))[:, :(B - 1) * 256 + 1024])
+    stream *= np.linspace(0.5, 1.5, stream.shape[1], dtype=np.float32)[None, :]      # no two frames alike
+    full = w.power_map_batch(stream, B)
+    assert full.shape == (B, 64) and np.all(np.isfinite(full)) and full.min() > 0
+    for b0, nb in [(0, 3), (510, 5), (1022, 4), (1097, 3)]:                          # across the chunk boundaries
+        part = w.power_map_batch(np.ascontiguousarray(stream[:, b0 * 256:(b0 + nb - 1) * 256 + 1024]), nb)
+        assert np.array_equal(full[b0:b0 + nb], part)
+
+
 def test_caller_supplied_tables_and_errors(bf, oracle):
     import bflk
     xyz = oracle.create_antenna()
