@@ -434,7 +434,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[0];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax);
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles);
     h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
     if (!h->tiles_usable) return BFLK_OK;
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape

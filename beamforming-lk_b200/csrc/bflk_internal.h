@@ -242,7 +242,7 @@ typedef void (*TileLaunchHook)(void *ctx, int kind, bool begin, cudaStream_t st)
 cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
                             void *hook_ctx = nullptr);
 int das_tile_max_span();
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span);
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0);
 size_t das_tile_packed_bytes(const TileArgs &a);
 
 // ---- das_bcast.cu -----------------------------------------------------------------------------------

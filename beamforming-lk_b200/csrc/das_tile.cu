@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     else if (tB < a.row_len) B.x = row[tB];
     char *dst = reinterpret_cast<char *>(a.packed) + ((size_t)pair * a.usable + s) * a.row_bytes + 16 * padded_chunk(ch);
     *reinterpret_cast<float4 *>(dst) = make_float4(A.x, B.x, A.y, B.y);
+    // also fill the pad chunk that follows every fourth chunk: whole 32-byte sectors reach DRAM, no partial writes
+    if ((ch & 3) == 3 && 16 * (padded_chunk(ch) + 2) <= a.row_bytes) *reinterpret_cast<float4 *>(dst + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------------
@@ -310,14 +312,26 @@ __global__ void finalize_kernel(const float *__restrict__ partial, int n_frames,
 // ---- host side ---------------------------------------------------------------------------------------------------
 int das_tile_max_span() { return 11; }
 
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span) {
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles) {
     TileGeometry g;
     g.stage_off = (history - max_delay) & ~1;
     g.nch = max_span <= 3 ? 6 : (max_span <= 7 ? 8 : 10);
-    g.warps = 12;  // measured on B200: 12 warps (3 per scheduler) beat 10 or 8 with more registers each
-    if (const char *env = getenv("BFLK_TILE_WARPS")) {  // tuning knob: 8, 10 or 12 compute warps per CTA
+    // Warps (= direction tiles) per CTA.  Measured on B200: 12 warps (3 per scheduler) beat 10 by ~15 %, so 12
+    // unless a small direction shard (multi-GPU) would leave the last CTA of every block pair mostly idle.
+    g.warps = 12;
+    if (n_tiles > 0) {
+        double best = 0.0;
+        const int cand[3] = {12, 11, 10};
+        const double tlp[3] = {1.0, 0.95, 0.88};
+        for (int i = 0; i < 3; i++) {
+            const int groups = (n_tiles + cand[i] - 1) / cand[i];
+            const double score = tlp[i] * n_tiles / (double)(groups * cand[i]);
+            if (score > best + 1e-9) { best = score; g.warps = cand[i]; }
+        }
+    }
+    if (const char *env = getenv("BFLK_TILE_WARPS")) {  // tuning knob
         const int v = atoi(env);
-        if (v == 8 || v == 10 || v == 12) g.warps = v;
+        if (v >= 10 && v <= 12) g.warps = v;
     }
     // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
     g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
@@ -398,8 +412,8 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         switch (a.geom.nch) {
 #define BFLK_LAUNCH(NCH)                                                              \
     switch (a.geom.warps) {                                                            \
-        case 8: e = launch_main<NCH, 8>(ks, grid, smem, st); break;                    \
         case 10: e = launch_main<NCH, 10>(ks, grid, smem, st); break;                  \
+        case 11: e = launch_main<NCH, 11>(ks, grid, smem, st); break;                  \
         default: e = launch_main<NCH, 12>(ks, grid, smem, st); break;                  \
     }
             case 6: BFLK_LAUNCH(6) break;
