@@ -98,62 +98,6 @@ struct KernelArgs {
     float norm;
 };
 
-template <int NCH>
-struct Window {
-    u64 w[2 * NCH];
-};
-
-// loads the NCH chunks of this lane's window; R = (first chunk index) & 3 fixes where the pad chunks fall
-template <int NCH, int R>
-__device__ __forceinline__ void load_window(u64 (&w)[2 * NCH], uint32_t addr) {
-#pragma unroll
-    for (int m = 0; m < NCH; m++) lds128(w[2 * m], w[2 * m + 1], addr + 16 * (m + ((R + m) >> 2)));
-}
-
-// acc[k] += fma(f, d[D + k], w[D + k + 1]) for the 8 sample pairs of this lane (delay.cpp:24)
-template <int NCH, int D>
-__device__ __forceinline__ void accumulate(u64 (&acc)[kK], const u64 (&w)[2 * NCH], const u64 (&d)[2 * NCH - 1], u64 ff) {
-    // software-pipelined by hand: the FADD2 of sample k issues four packed instructions after its FFMA2,
-    // so a single warp never waits on the FMA latency
-    u64 t[kK];
-#pragma unroll
-    for (int k = 0; k < 4; k++) t[k] = fma2(ff, d[D + k], w[D + k + 1]);
-#pragma unroll
-    for (int k = 0; k < kK; k++) {
-        acc[k] = add2(acc[k], t[k]);
-        if (k + 4 < kK) t[k + 4] = fma2(ff, d[D + k + 4], w[D + k + 5]);
-    }
-}
-
-// Warp-uniform dispatch on delta as a binary tree over its bits: predicated direct branches instead of a
-// jump-table load + indirect branch (the table load and BRX resolve dominated the first version's stalls).
-// The four bit predicates are formed together before the first branch so the branches do not wait on them.
-template <int NCH, int D0, int BITS>
-__device__ __forceinline__ void accumulate_tree(const bool (&bits)[4], u64 (&acc)[kK], const u64 (&w)[2 * NCH],
-                                                const u64 (&d)[2 * NCH - 1], u64 ff) {
-    constexpr int kMax = 2 * NCH - 9;  // largest delta whose window still fits the loaded chunks
-    if constexpr (D0 > kMax) {
-        return;
-    } else if constexpr (BITS == 0) {
-        accumulate<NCH, D0>(acc, w, d, ff);
-    } else {
-        constexpr int bit = 1 << (BITS - 1);
-        if constexpr (D0 + bit > kMax) {
-            accumulate_tree<NCH, D0, BITS - 1>(bits, acc, w, d, ff);
-        } else {
-            if (bits[BITS - 1]) accumulate_tree<NCH, D0 + bit, BITS - 1>(bits, acc, w, d, ff);
-            else accumulate_tree<NCH, D0, BITS - 1>(bits, acc, w, d, ff);
-        }
-    }
-}
-
-template <int NCH>
-__device__ __forceinline__ void accumulate_dyn(uint32_t delta, u64 (&acc)[kK], const u64 (&w)[2 * NCH],
-                                               const u64 (&d)[2 * NCH - 1], float f) {
-    const bool bits[4] = {(delta & 1u) != 0, (delta & 2u) != 0, (delta & 4u) != 0, (delta & 8u) != 0};
-    accumulate_tree<NCH, 0, 4>(bits, acc, w, d, dup2(f));
-}
-
 #include "das_tile_asm.inc"
 
 template <int NCH, int kWarps>
@@ -215,38 +159,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * (int)sizeof(TileEntry);
         const int nc = min(kCC, a.usable - st * kCC);
         if (active) {
-            uint32_t e0, e1, n0, n1;
-            float f0, f1, f2, f3, g0, g1, g2, g3;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(tiles_s));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(tiles_s + 16));
+            uint32_t e0, e1;
+            float f0, f1, f2, f3;
+            uint32_t ent = tiles_s, row = rows_s + lane_off;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(ent));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(ent + 16));
 #pragma unroll 1
             for (int c = 0; c < nc; c++) {
-                // the next channel's table entry is fetched one iteration ahead (its latency hides behind this channel)
-                const uint32_t nt = tiles_s + 32 * min(c + 1, nc - 1);
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n0), "=r"(n1) : "r"(nt));
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3) : "r"(nt + 16));
-                const uint32_t addr = rows_s + c * a.row_bytes + e0 + lane_off;
-                u64 w[2 * NCH];
-                {
-                    // chunk m of the window sits at padded chunk m + ((r + m) >> 2), r = (first chunk) & 3: the pad
-                    // correction is 16 * (m >> 2) plus 16 more when r + (m & 3) >= 4 -> one of two base registers
-                    const uint32_t r = e1 >> 24, hi = addr + 16;
-                    const uint32_t base[4] = {addr, r >= 3 ? hi : addr, r >= 2 ? hi : addr, r >= 1 ? hi : addr};
-#pragma unroll
-                    for (int m = 0; m < NCH; m++) lds128(w[2 * m], w[2 * m + 1], base[m & 3] + 16 * (m + (m >> 2)));
-                }
-                u64 d[2 * NCH - 1];
-#pragma unroll
-                for (int j = 0; j < 2 * NCH - 1; j++) d[j] = sub2(w[j], w[j + 1]);  // s[i] - s[i+1], once per window
-#ifdef BFLK_TILE_CPP_DISPATCH
-                accumulate_dyn<NCH>(e1 & 63, acc[0], w, d, f0);
-                accumulate_dyn<NCH>((e1 >> 6) & 63, acc[1], w, d, f1);
-                accumulate_dyn<NCH>((e1 >> 12) & 63, acc[2], w, d, f2);
-                accumulate_dyn<NCH>((e1 >> 18) & 63, acc[3], w, d, f3);
-#else
-                tile_channel_asm(acc, w, d, f0, f1, f2, f3, e1);  // hand-scheduled PTX, tools/gen_tile_asm.py
-#endif
-                e0 = n0; e1 = n1; f0 = g0; f1 = g1; f2 = g2; f3 = g3;
+                // window loads, differences, four accumulate bodies, prefetch of entry c + 1 into e0..f3 (the read past
+                // the last entry of a stage stays inside this CTA's shared memory and is never used)
+                ent += 32;
+                tile_channel_step<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
+                row += a.row_bytes;
             }
         }
         __syncwarp();
@@ -316,22 +240,24 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     TileGeometry g;
     g.stage_off = (history - max_delay) & ~1;
     g.nch = max_span <= 3 ? 6 : (max_span <= 7 ? 8 : 10);
-    // Warps (= direction tiles) per CTA.  Measured on B200: 12 warps (3 per scheduler) beat 10 by ~15 %, so 12
-    // unless a small direction shard (multi-GPU) would leave the last CTA of every block pair mostly idle.
+    // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
+    // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
+    // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
+    // spill).  Smaller CTAs only when a small direction shard (multi-GPU) would leave the last CTA mostly idle.
+    const int n_cand = 4;
+    const int cand[n_cand] = {16, 12, 11, 10};
+    const double tlp[n_cand] = {g.nch == 6 ? 1.05 : 0.0, 1.0, 0.95, 0.88};
     g.warps = 12;
-    if (n_tiles > 0) {
-        double best = 0.0;
-        const int cand[3] = {12, 11, 10};
-        const double tlp[3] = {1.0, 0.95, 0.88};
-        for (int i = 0; i < 3; i++) {
-            const int groups = (n_tiles + cand[i] - 1) / cand[i];
-            const double score = tlp[i] * n_tiles / (double)(groups * cand[i]);
-            if (score > best + 1e-9) { best = score; g.warps = cand[i]; }
-        }
+    double best = 0.0;
+    for (int i = 0; i < n_cand; i++) {
+        const int tiles = n_tiles > 0 ? n_tiles : 1 << 20;
+        const int groups = (tiles + cand[i] - 1) / cand[i];
+        const double score = tlp[i] * tiles / (double)(groups * cand[i]);
+        if (score > best + 1e-9) { best = score; g.warps = cand[i]; }
     }
     if (const char *env = getenv("BFLK_TILE_WARPS")) {  // tuning knob
         const int v = atoi(env);
-        if (v >= 10 && v <= 12) g.warps = v;
+        if ((v >= 10 && v <= 12) || v == 16) g.warps = v;
     }
     // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
     g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
@@ -414,6 +340,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     switch (a.geom.warps) {                                                            \
         case 10: e = launch_main<NCH, 10>(ks, grid, smem, st); break;                  \
         case 11: e = launch_main<NCH, 11>(ks, grid, smem, st); break;                  \
+        case 16: e = launch_main<NCH, 16>(ks, grid, smem, st); break;                  \
         default: e = launch_main<NCH, 12>(ks, grid, smem, st); break;                  \
     }
             case 6: BFLK_LAUNCH(6) break;

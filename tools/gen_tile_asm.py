@@ -1,129 +1,194 @@
 #!/usr/bin/env python
-"""Generates beamforming-lk_b200/csrc/das_tile_asm.inc: the per-channel accumulate step of das_tile as
-hand-scheduled inline PTX, one block per channel covering the four directions of a tile.
+"""Generates beamforming-lk_b200/csrc/das_tile_asm.inc: one channel step of das_tile as hand-written PTX.
 
-Why PTX: the step is "for each direction, jump to the body whose register operands match the direction's
-offset inside the shared window".  Written in C++ the compiler re-derives each branch predicate right before
-its branch (a 20+ cycle ISETP -> BRA dependency per tree level) and wraps every tree in divergence
-bookkeeping (BSSY / BSYNC).  Here the bit predicates of a direction are formed together up front, the
-branches are `bra.uni` (the offsets are warp-uniform by construction) and the FFMA2 / FADD2 pairs are
-software-pipelined four deep.
+One asm block per (warp, channel) does: window loads (LDS.128 with the pad correction folded into two base
+registers), the differences s[i] - s[i+1] (once per window), then for each of the tile's four directions a
+jump to the body whose register operands match the direction's offset inside the window, and finally the
+prefetch of the next channel's table entry into the same registers.
+
+Why PTX instead of C++ (measured on B200, profiles/README.md):
+ * C++ re-derives every branch predicate right before its branch (a ~20-cycle ISETP -> BRA dependency per
+   tree level).  Here the bit predicates of a direction are formed one direction ahead (two predicate sets).
+ * `bra.uni` + no join points ("chain"): each case body ends with the NEXT direction's dispatch, so a
+   direction costs only its tree branches; bodies are shared, only the small trees are replicated.
+ * the table-entry prefetch lands in place (no register moves), the loop around the block is two adds.
+The kernel is issue-bound (an FFMA2 / FADD2 holds the issue port two cycles), so every instruction removed
+from this block is throughput.
+
+Rejected variants, kept behind flags: BFLK_GEN_VOTE=1 (vote-uniform predicates, -7 %), BFLK_GEN_BRX=1
+(brx.idx jump table, -9 .. -22 %), BFLK_GEN_CHAIN=0 (join after every direction).
 
 usage: python tools/gen_tile_asm.py > beamforming-lk_b200/csrc/das_tile_asm.inc
 """
-K = 8
-
-
 import os
-VOTE = os.environ.get('BFLK_GEN_VOTE', '0') == '1'   # measured slower on B200 (extra VOTE + BRA.DIV per direction)
-BRX = os.environ.get('BFLK_GEN_BRX', '0') == '1'     # indexed jump instead of the bit tree
-DEPTH = 4   # FFMA2 -> FADD2 software-pipeline depth (temporaries); set per variant in gen()
 
+K = 8
+VOTE = os.environ.get("BFLK_GEN_VOTE", "0") == "1"
+BRX = os.environ.get("BFLK_GEN_BRX", "0") == "1"
+CHAIN = os.environ.get("BFLK_GEN_CHAIN", "1") == "1"
 
-def body(r, D, lines, ind="    "):
-    """acc[r][k] = acc[r][k] + fma(ff, d[D+k], w[D+k+1]), k = 0..7 (delay.cpp:24), pipelined DEPTH deep."""
-    def fma(t, k):
-        lines.append(f"{ind}fma.rn.f32x2 t{t}, ff, %{DOP(D + k)}, %{WOP(D + k + 1)};")
-
-    def add(k, t):
-        lines.append(f"{ind}add.rn.f32x2 %{AOP(r, k)}, %{AOP(r, k)}, t{t};")
-    for k in range(DEPTH):
-        fma(k, k)
-    for k in range(K):
-        add(k, k % DEPTH)
-        if k + DEPTH < K:
-            fma(k % DEPTH, k + DEPTH)
+# operand numbers of the asm block: acc[4][8] "+l" 0..31, e0 32, e1 33 ("+r"), f0..f3 34..37 ("+f"),
+# row 38 ("r": shared address of this lane's row start), nxt 39 ("r": shared address of the next entry)
+A = lambda r, k: f"%{r * K + k}"
+E0, E1, ROW, NXT = "%32", "%33", "%38", "%39"
+F = lambda r: f"%{34 + r}"
 
 
 def gen(nch):
-    global AOP, WOP, DOP, DEPTH
-    DEPTH = 8 if nch <= 8 else 4
-    nw = 2 * nch           # w[0 .. 2nch-1]; w[0] is never an FMA operand
-    nd = 2 * nch - 1       # d[0 .. 2nch-2]
-    kmax = 2 * nch - 9
+    nw, nd = 2 * nch, 2 * nch - 1
+    kmax = 2 * nch - 9                      # largest delta whose 9-pair window fits the loaded chunks
     nbits = max(1, kmax.bit_length())
-    # operand numbering: acc (32, "+l"), w[1..nw-1], d[0..nd-1], f0..f3, e1
-    AOP = lambda r, k: r * K + k
-    WOP = lambda j: 32 + (j - 1)
-    DOP = lambda j: 32 + (nw - 1) + j
-    FOP = lambda r: 32 + (nw - 1) + nd + r
-    EOP = 32 + (nw - 1) + nd + 4
-    L = []
-    L.append("{")
-    dbl = 2 * nbits <= 6               # two predicate sets fit the 7 predicate registers
+    depth = 8 if nch <= 8 else 4            # FFMA2 -> FADD2 software-pipeline depth (temporaries)
+    dbl = 2 * nbits <= 6                    # two predicate sets fit the 7 predicate registers
+    chain = CHAIN and dbl and not BRX
     sets = ["pa", "pb"] if dbl else ["pa", "pa"]
-    L.append(f"    .reg .pred pa<{nbits}>, pb<{nbits}>;")
-    L.append("    .reg .b32 x;")
-    L.append(f"    .reg .b64 ff, t<{DEPTH}>;")
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        """acc[r][k] = acc[r][k] + fma(f, d[D+k], w[D+k+1]), k = 0..7  (delay.cpp:24), pipelined."""
+        fma = lambda t, k: emit(f"    fma.rn.f32x2 t{t}, ff, d{D + k}, w{D + k + 1};")
+        add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
+        for k in range(depth):
+            fma(k, k)
+        for k in range(K):
+            add(k, k % depth)
+            if k + depth < K:
+                fma(k % depth, k + depth)
 
     def preds(r, ps):
-        L.append(f"    // predicates of direction {r}: bits of delta = (e1 >> {6 * r}) & 63")
         for b in range(nbits):
-            L.append(f"    and.b32 x, %{EOP}, {1 << (6 * r + b)};")
-            L.append(f"    setp.ne.b32 {ps}{b}, x, 0;")
+            emit(f"    and.b32 x, {E1}, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 {ps}{b}, x, 0;")
             if VOTE:
-                # the offsets are warp-uniform by construction; a vote makes that visible to ptxas, which then
-                # uses uniform predicates + BRA.U and drops the BSSY / BSYNC reconvergence bookkeeping
-                L.append(f"    vote.sync.any.pred {ps}{b}, {ps}{b}, 0xffffffff;")
+                emit(f"    vote.sync.any.pred {ps}{b}, {ps}{b}, 0xffffffff;")
 
-    preds(0, sets[0])
-    for r in range(4):
-        ps = sets[r % 2]
-        # the next direction's predicates are formed before this direction's body runs, so its branches never
-        # wait on a compare (when both sets fit the predicate file)
-        if dbl and r + 1 < 4:
-            preds(r + 1, sets[(r + 1) % 2])
-        elif not dbl and r > 0:
-            preds(r, ps)
-        L.append(f"    // ---- direction {r}")
-        L.append(f"    mov.b64 ff, {{%{FOP(r)}, %{FOP(r)}}};")
-        tree_start = len(L)
+    def setf(r):
+        emit(f"    mov.b64 ff, {{{F(r)}, {F(r)}}};")
 
-        def tree(d0, bit):
-            # dispatches among deltas d0 .. d0 + 2^(bit+1) - 1 (clipped to kmax)
+    def prefetch():
+        # e0, e1, f0..f3 are dead from here on: fetch the next channel's entry into them
+        emit(f"    ld.shared.v2.u32 {{{E0}, {E1}}}, [{NXT}];")
+        emit(f"    ld.shared.v4.f32 {{{F(0)}, {F(1)}, {F(2)}, {F(3)}}}, [{NXT}+16];")
+
+    emit("{")
+    emit(f"    .reg .pred pa<{nbits}>, pb<{nbits}>, q<4>;")
+    emit("    .reg .b32 x, rr, a<4>;")
+    emit(f"    .reg .b64 ff, t<{depth}>, w<{nw}>, d<{nd}>;")
+    # ---- window: chunk m sits at padded chunk m + ((r + m) >> 2), r = bits 24-25 of e1 -----------------
+    emit(f"    add.u32 a0, {ROW}, {E0};")
+    emit(f"    shr.u32 rr, {E1}, 24;")
+    emit("    add.u32 x, a0, 16;")
+    for cls, thr in ((1, 3), (2, 2), (3, 1)):   # chunk class m & 3 needs the +16 when r >= 4 - (m & 3)
+        emit(f"    setp.ge.u32 q{cls}, rr, {thr};")
+        emit(f"    selp.u32 a{cls}, x, a0, q{cls};")
+    for m in range(nch):
+        emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [a{m & 3}+{16 * (m + (m >> 2))}];")
+    if chain:
+        preds(0, sets[0])
+        preds(1, sets[1])
+    else:
+        preds(0, sets[0])
+    for j in range(nd):
+        emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")       # s[i] - s[i+1], once per window
+
+    if chain:
+        uid = [0]
+
+        def jump_tree(r, ps, d0, bit):
             if bit < 0:
-                body(r, d0, L)
-                L.append(f"    bra.uni J{r};")
+                emit(f"    bra.uni B{r}_{d0};")
                 return
             hi = d0 + (1 << bit)
             if hi > kmax:
-                tree(d0, bit - 1)
+                jump_tree(r, ps, d0, bit - 1)
                 return
-            L.append(f"    @{ps}{bit} bra.uni T{r}_{hi}_{bit};")
-            tree(d0, bit - 1)
-            L.append(f"T{r}_{hi}_{bit}:")
-            tree(hi, bit - 1)
-        if BRX:
-            # undo the tree: one indexed jump (LDC + BRX) to the case body
-            del L[tree_start:]
-            labels = ", ".join(f"C{r}_{dd}" for dd in range(kmax + 1))
-            L.append(f"    bfe.u32 x, %{EOP}, {6 * r}, 6;")
-            L.append(f"    min.u32 x, x, {kmax};")
-            L.append(f"TS{r}: .branchtargets {labels};")
-            L.append(f"    brx.idx.uni x, TS{r};")
+            uid[0] += 1
+            lab = f"N{uid[0]}"
+            emit(f"    @{ps}{bit} bra.uni {lab};")
+            jump_tree(r, ps, d0, bit - 1)
+            emit(f"{lab}:")
+            jump_tree(r, ps, hi, bit - 1)
+
+        setf(0)
+        jump_tree(0, sets[0], 0, nbits - 1)
+        for r in range(4):
             for dd in range(kmax + 1):
-                L.append(f"C{r}_{dd}:")
-                body(r, dd, L)
-                L.append(f"    bra.uni J{r};")
-        else:
-            tree(0, nbits - 1)
-        L.append(f"J{r}:")
-    L.append("}")
+                emit(f"B{r}_{dd}:")
+                if r == 3:
+                    prefetch()
+                body(r, dd)
+                if r == 3:
+                    emit("    bra.uni DONE;")
+                    continue
+                if r + 2 < 4:
+                    preds(r + 2, sets[r % 2])          # the set this direction just consumed
+                setf(r + 1)
+                jump_tree(r + 1, sets[(r + 1) % 2], 0, nbits - 1)
+        emit("DONE:")
+    else:
+        for r in range(4):
+            ps = sets[r % 2]
+            if dbl and r + 1 < 4:
+                preds(r + 1, sets[(r + 1) % 2])
+            elif not dbl and r > 0:
+                preds(r, ps)
+            setf(r)
+            if r == 3:
+                prefetch()
+            if BRX:
+                labels = ", ".join(f"C{r}_{dd}" for dd in range(kmax + 1))
+                emit(f"    bfe.u32 x, {E1}, {6 * r}, 6;")
+                emit(f"    min.u32 x, x, {kmax};")
+                emit(f"TS{r}: .branchtargets {labels};")
+                emit(f"    brx.idx.uni x, TS{r};")
+                for dd in range(kmax + 1):
+                    emit(f"C{r}_{dd}:")
+                    body(r, dd)
+                    emit(f"    bra.uni J{r};")
+            else:
+                def tree(d0, bit):
+                    if bit < 0:
+                        body(r, d0)
+                        emit(f"    bra.uni J{r};")
+                        return
+                    hi = d0 + (1 << bit)
+                    if hi > kmax:
+                        tree(d0, bit - 1)
+                        return
+                    emit(f"    @{ps}{bit} bra.uni T{r}_{hi}_{bit};")
+                    tree(d0, bit - 1)
+                    emit(f"T{r}_{hi}_{bit}:")
+                    tree(hi, bit - 1)
+                tree(0, nbits - 1)
+            emit(f"J{r}:")
+    emit("}")
+    if BRX or (not chain and not dbl):
+        # with a single predicate set direction 3's predicates read e1 before the prefetch overwrites it: fine,
+        # the prefetch is emitted after preds(3)
+        pass
     asm = "\n".join(f'        "{ln}\\n"' for ln in L)
-    outs = ", ".join(f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K))
-    ins = ", ".join([f'"l"(w[{j}])' for j in range(1, nw)] + [f'"l"(d[{j}])' for j in range(nd)] +
-                    [f'"f"(f{r})' for r in range(4)] + ['"r"(e1)'])
-    return f"""// NCH = {nch}: window of {nw} sample pairs, deltas 0..{kmax}
-__device__ __forceinline__ void tile_channel_asm(u64 (&acc)[4][{K}], const u64 (&w)[{nw}], const u64 (&d)[{nd}],
-                                                 float f0, float f1, float f2, float f3, uint32_t e1) {{
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K)] + ['"+r"(e0)', '"+r"(e1)'] +
+                     [f'"+f"(f{r})' for r in range(4)])
+    return f"""// NCH = {nch}: window of {nw} sample pairs, deltas 0..{kmax}, {'chained' if chain else 'joined'} dispatch
+template <>
+__device__ __forceinline__ void tile_channel_step<{nch}>(u64 (&acc)[4][{K}], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
+                                                     float &f2, float &f3, uint32_t row, uint32_t nxt) {{
     asm volatile(
 {asm}
         : {outs}
-        : {ins});
+        : "r"(row), "r"(nxt)
+        : "memory");
 }}
 """
 
 
 print("// GENERATED by tools/gen_tile_asm.py -- do not edit.  See that script for the why.")
+print("""// One channel of one tile: window loads, differences, the four directions' accumulate bodies, and the prefetch of
+// the next channel's table entry (e0 = window byte offset, e1 = 4 x 6-bit deltas | pad phase << 24, f = fractions).
+template <int NCH>
+__device__ __forceinline__ void tile_channel_step(u64 (&acc)[4][8], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
+                                                  float &f2, float &f3, uint32_t row, uint32_t nxt);
+""")
 for nch in (6, 8, 10):
     print(gen(nch))
