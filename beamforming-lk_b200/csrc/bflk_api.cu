@@ -7,6 +7,7 @@
 // (src/aw_processing_unit/aw_processing_unit.cpp:148-200).  Everything O(D*C) or larger runs on the GPU.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "bflk_internal.h"
@@ -424,17 +425,30 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, h->d_misc.reserve(4));
     BFLK_CUDA(h, h->p_misc.reserve(4));
     const int stage_off = das_tile_geometry(h->cfg.history, h->max_delay, 0).stage_off;
-    // pass 1: largest offset spread inside a tile -> which kernel variant (window chunks, warps per CTA)
+    // pass 1: largest offset spread per tiling mode -> which kernel variant (window chunks, warps per CTA).
+    // mode 0 shares one window among the 2x2 tile; modes 1 / 2 share one window per direction pair (coarse grids).
     BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
-    BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, stage_off, 1, nullptr, h->d_tile_dirs.p, n_tiles,
-                                    h->d_misc.p, h->stream));
-    h->launches++;
-    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    for (int mode = 0; mode < 3; mode++) {
+        BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
+                                        h->dir_first, h->dir_count, stage_off, 1, mode, nullptr, nullptr, n_tiles,
+                                        h->d_misc.p, h->stream));
+        h->launches++;
+    }
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int span0 = h->p_misc.p[0], span1 = h->p_misc.p[1], span2 = h->p_misc.p[2];
+    // one shared window while the 2x2 spread fits the 6- or 8-chunk variant; beyond that (coarse grid, long array) the
+    // direction pairs along the array's short axis still fit a 6- / 7-chunk window each: measured faster than the
+    // 10-chunk single window (fewer dispatch cases, smaller code, more resident warps)
+    int mode = 0;
+    if (span0 > 7 && std::min(span1, span2) <= 5) mode = span1 <= span2 ? 1 : 2;
+    if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
+        const int v = atoi(env);
+        if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
+    }
     h->n_tiles = n_tiles;
-    h->tile_smax = h->p_misc.p[0];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles);
+    h->tile_smax = h->p_misc.p[mode];
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode);
     h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
     if (!h->tiles_usable) return BFLK_OK;
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
@@ -442,7 +456,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, h->d_tiles.reserve(entries));
     BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * sizeof(TileEntry), h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.warps, h->d_tiles.p,
+                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.warps, mode, h->d_tiles.p,
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -23,8 +23,9 @@ struct DirTrig {
 // Packed per-(direction tile, usable channel) entry of the register-tiled kernel (das_tile.cu).
 // base: even-aligned smallest offset of the tile's directions, delta[r] = offset[r] - base.
 struct __align__(16) TileEntry {
-    uint32_t win_off;   // byte offset of lane 0's window inside a packed row (padded layout)
-    uint32_t deltas;    // 4 x 6 bit: delta of direction r in bits [6r, 6r+6); bits 24-25: (first chunk) & 3
+    uint32_t win_off;   // byte offset of lane 0's window inside a packed row (padded layout); two 16-bit offsets
+                        // (window A | window B << 16) in the two-window modes
+    uint32_t deltas;    // 4 x 6 bit: delta of slot r in bits [6r, 6r+6); bits 24-25 (26-27): (first chunk) & 3 of window A (B)
     int32_t span;       // max delta of the tile for this channel
     int32_t reserved;
     float frac[4];      // fractional delays of the 4 directions
@@ -46,6 +47,7 @@ struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
     int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
     int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
+    int mode = 0;        // 0: one window per tile; 1 / 2: one window per direction pair (rows of a column / columns of a row)
     int row_chunks = 0;  // logical chunks per packed row
     int row_bytes = 0;   // padded bytes per packed row
 };
@@ -195,8 +197,8 @@ cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d
 cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st);
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, int warps, TileEntry *d_tiles,
-                               int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st);
+                               int rows, int cols, int first, int count, int stage_off, int warps, int mode,
+                               TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
 struct GenericArgs {
@@ -242,7 +244,7 @@ typedef void (*TileLaunchHook)(void *ctx, int kind, bool begin, cudaStream_t st)
 cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
                             void *hook_ctx = nullptr);
 int das_tile_max_span();
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0);
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0);
 size_t das_tile_packed_bytes(const TileArgs &a);
 
 // ---- das_bcast.cu -----------------------------------------------------------------------------------

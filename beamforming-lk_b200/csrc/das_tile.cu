@@ -100,7 +100,8 @@ struct KernelArgs {
 
 #include "das_tile_asm.inc"
 
-template <int NCH, int kWarps>
+// DUAL: two NCH-chunk windows per channel, one per direction pair (tile tables built with mode 1 / 2), NCH 6 or 7
+template <int NCH, int kWarps, bool DUAL = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * 32 } then barriers
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
                 // window loads, differences, four accumulate bodies, prefetch of entry c + 1 into e0..f3 (the read past
                 // the last entry of a stage stays inside this CTA's shared memory and is never used)
                 ent += 32;
-                tile_channel_step<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
+                if constexpr (DUAL) tile_channel_step_dual<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
+                else tile_channel_step<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
                 row += a.row_bytes;
             }
         }
@@ -236,10 +238,11 @@ __global__ void finalize_kernel(const float *__restrict__ partial, int n_frames,
 // ---- host side ---------------------------------------------------------------------------------------------------
 int das_tile_max_span() { return 11; }
 
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles) {
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode) {
     TileGeometry g;
+    g.mode = mode;
     g.stage_off = (history - max_delay) & ~1;
-    g.nch = max_span <= 3 ? 6 : (max_span <= 7 ? 8 : 10);
+    g.nch = max_span <= 3 ? 6 : (mode != 0 ? 7 : (max_span <= 7 ? 8 : 10));  // two-window modes: spans up to 5
     // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
     // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
     // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
@@ -265,11 +268,11 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     return g;
 }
 
-template <int NCH, int WARPS>
+template <int NCH, int WARPS, bool DUAL = false>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    das_tile_kernel<NCH, WARPS><<<grid, WARPS * 32, smem, st>>>(k);
+    das_tile_kernel<NCH, WARPS, DUAL><<<grid, WARPS * 32, smem, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -335,6 +338,22 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (e != cudaSuccess) return e;
         dim3 grid((a.n_tiles + kWarps - 1) / kWarps, np);
         if (hook) hook(hook_ctx, 0, true, st);
+        if (a.geom.mode != 0) {
+            if (a.geom.nch == 6) {
+                switch (a.geom.warps) {
+                    case 10: e = launch_main<6, 10, true>(ks, grid, smem, st); break;
+                    case 11: e = launch_main<6, 11, true>(ks, grid, smem, st); break;
+                    case 12: e = launch_main<6, 12, true>(ks, grid, smem, st); break;
+                    default: e = launch_main<6, 16, true>(ks, grid, smem, st); break;
+                }
+            } else {
+                switch (a.geom.warps) {
+                    case 10: e = launch_main<7, 10, true>(ks, grid, smem, st); break;
+                    case 11: e = launch_main<7, 11, true>(ks, grid, smem, st); break;
+                    default: e = launch_main<7, 12, true>(ks, grid, smem, st); break;
+                }
+            }
+        } else
         switch (a.geom.nch) {
 #define BFLK_LAUNCH(NCH)                                                              \
     switch (a.geom.warps) {                                                            \

@@ -88,9 +88,13 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // Tiles are 2x2 blocks of grid directions (r0..r0+1, c0..c0+1).  A handle's direction range
 // [first, first+count) is a run of the row-major grid; tiles are enumerated over the rows the range
 // touches and directions outside the range get tile_dirs = -1 (computed but not stored).
+// mode 0: one window shared by the four directions of the tile.
+// mode 1 / 2: two windows, each shared by a PAIR of directions (1: the two rows of a grid column, 2: the two columns
+// of a grid row); directions are stored in "slot" order -- slots 0,1 use window A, slots 2,3 window B -- and
+// tile_dirs follows the same order.  maxspan[mode] receives the largest delta of that mode.
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
-                                   int count, int stage_off, int warps, TileEntry *__restrict__ tiles,
+                                   int count, int stage_off, int warps, int mode, TileEntry *__restrict__ tiles,
                                    int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
                                    int32_t *__restrict__ maxspan) {
     const int t = blockIdx.x;
@@ -98,62 +102,80 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
     const int tr = t / tile_cols, tc = t % tile_cols;
     int dirs[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int slot = 0; slot < 4; slot++) {
+        // grid position q = 2 * row + col of the direction in this slot
+        const int q = mode == 1 ? ((slot & 1) << 1 | (slot >> 1)) : slot;
         int r = row0 + 2 * tr + (q >> 1), c = 2 * tc + (q & 1);
-        int g = (r < rows && c < cols) ? r * cols + c : -1;
-        dirs[q] = g;
+        dirs[slot] = (r < rows && c < cols) ? r * cols + c : -1;
     }
-    // a direction that does not exist (odd grid edge) aliases the tile's first direction
+    // a direction that does not exist (odd grid edge) aliases the first existing direction of the tile
     int ref = dirs[0];
-    if (threadIdx.x < 4) {
+#pragma unroll
+    for (int slot = 1; slot < 4; slot++)
+        if (ref < 0) ref = dirs[slot];
+    if (threadIdx.x < 4 && tile_dirs) {
         int g = dirs[threadIdx.x];
-        int local = (g >= first && g < first + count) ? g - first : -1;
-        tile_dirs[4 * t + threadIdx.x] = local;
+        tile_dirs[4 * t + threadIdx.x] = (g >= first && g < first + count) ? g - first : -1;
     }
     int span_max = 0;
     for (int s = threadIdx.x; s < usable; s += blockDim.x) {
         const int c = index[s];
         int o[4];
-        float f[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            int g = dirs[q] >= 0 ? dirs[q] : ref;
-            o[q] = off[(size_t)g * C + c];
-            f[q] = frac[(size_t)g * C + c];
-        }
-        int mn = min(min(o[0], o[1]), min(o[2], o[3]));
-        int base = mn & ~1;  // even: the pair-interleaved window is fetched with 16-byte loads
-        const int cb = (base - stage_off) >> 1;  // first 16-byte chunk of lane 0's window
         TileEntry e;
-        e.win_off = 16u * (unsigned)(cb + (cb >> 2));  // one pad chunk after every four
-        e.reserved = 0;
-        unsigned packed = (unsigned)(cb & 3) << 24;
-        int span = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            int dlt = o[q] - base;
-            span = max(span, dlt);
-            packed |= (unsigned)(dlt & 63) << (6 * q);
-            e.frac[q] = f[q];
+        for (int slot = 0; slot < 4; slot++) {
+            int g = dirs[slot] >= 0 ? dirs[slot] : ref;
+            o[slot] = off[(size_t)g * C + c];
+            e.frac[slot] = frac[(size_t)g * C + c];
+        }
+        unsigned packed = 0;
+        int span = 0;
+        if (mode == 0) {
+            const int base = min(min(o[0], o[1]), min(o[2], o[3])) & ~1;  // even: windows are fetched with 16-byte loads
+            const int cb = (base - stage_off) >> 1;                      // first 16-byte chunk of lane 0's window
+            e.win_off = 16u * (unsigned)(cb + (cb >> 2));                // one pad chunk after every four
+            packed = (unsigned)(cb & 3) << 24;
+#pragma unroll
+            for (int slot = 0; slot < 4; slot++) {
+                const int dlt = o[slot] - base;
+                span = max(span, dlt);
+                packed |= (unsigned)(dlt & 63) << (6 * slot);
+            }
+        } else {
+            e.win_off = 0;
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const int base = min(o[2 * w], o[2 * w + 1]) & ~1;
+                const int cb = (base - stage_off) >> 1;
+                e.win_off |= (16u * (unsigned)(cb + (cb >> 2))) << (16 * w);
+                packed |= (unsigned)(cb & 3) << (24 + 2 * w);
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int dlt = o[2 * w + k] - base;
+                    span = max(span, dlt);
+                    packed |= (unsigned)(dlt & 63) << (6 * (2 * w + k));
+                }
+            }
         }
         e.deltas = packed;
         e.span = span;
+        e.reserved = 0;
         const int n_stage = (usable + kTileCC - 1) / kTileCC;
         if (tiles)
             tiles[((size_t)(t / warps) * n_stage + s / kTileCC) * (warps * kTileCC) + (t % warps) * kTileCC + s % kTileCC] = e;
         span_max = max(span_max, span);
     }
     for (int o = 16; o > 0; o >>= 1) span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(maxspan, span_max);
+    if ((threadIdx.x & 31) == 0) atomicMax(maxspan + mode, span_max);
 }
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, int warps, TileEntry *d_tiles,
-                               int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
+                               int rows, int cols, int first, int count, int stage_off, int warps, int mode,
+                               TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
     build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
-                                                warps, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+                                                warps, mode, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

@@ -183,6 +183,130 @@ __device__ __forceinline__ void tile_channel_step<{nch}>(u64 (&acc)[4][{K}], uin
 """
 
 
+def gen_dual(nch):
+    """Two windows per channel, each shared by a pair of directions (slots 0,1 -> window A, slots 2,3 -> window B),
+    processed one after the other through the same registers.  For coarse grids whose 2x2 tiles spread over more
+    samples than one 6-chunk window holds: the pairs along the array's short axis still fit, the kernel keeps the
+    small 4-case dispatch, 128 registers and 16 warps."""
+    nw, nd = 2 * nch, 2 * nch - 1
+    kmax = 2 * nch - 9
+    nbits = max(1, kmax.bit_length())
+    depth = 8
+    assert 2 * nbits <= 6
+    sets = ["pa", "pb"]
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        fma = lambda t, k: emit(f"    fma.rn.f32x2 t{t}, ff, d{D + k}, w{D + k + 1};")
+        add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
+        for k in range(depth):
+            fma(k, k)
+        for k in range(K):
+            add(k, k % depth)
+            if k + depth < K:
+                fma(k % depth, k + depth)
+
+    def preds(r, ps):
+        for b in range(nbits):
+            emit(f"    and.b32 x, {E1}, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 {ps}{b}, x, 0;")
+
+    def setf(r):
+        emit(f"    mov.b64 ff, {{{F(r)}, {F(r)}}};")
+
+    def window(w):
+        # window w: byte offset in the low / high half of e0, pad phase in bits 24-25 / 26-27 of e1
+        if w == 0:
+            emit(f"    and.b32 x, {E0}, 0xffff;")
+        else:
+            emit(f"    shr.u32 x, {E0}, 16;")
+        emit(f"    add.u32 a0, {ROW}, x;")
+        emit(f"    bfe.u32 rr, {E1}, {24 + 2 * w}, 2;")
+        emit("    add.u32 x, a0, 16;")
+        for cls, thr in ((1, 3), (2, 2), (3, 1)):
+            emit(f"    setp.ge.u32 q{cls}, rr, {thr};")
+            emit(f"    selp.u32 a{cls}, x, a0, q{cls};")
+        for m in range(nch):
+            emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [a{m & 3}+{16 * (m + (m >> 2))}];")
+
+    def subs():
+        for j in range(nd):
+            emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")
+
+    uid = [0]
+
+    def jump_tree(r, ps, d0, bit):
+        if bit < 0:
+            emit(f"    bra.uni B{r}_{d0};")
+            return
+        hi = d0 + (1 << bit)
+        if hi > kmax:
+            jump_tree(r, ps, d0, bit - 1)
+            return
+        uid[0] += 1
+        lab = f"N{uid[0]}"
+        emit(f"    @{ps}{bit} bra.uni {lab};")
+        jump_tree(r, ps, d0, bit - 1)
+        emit(f"{lab}:")
+        jump_tree(r, ps, hi, bit - 1)
+
+    emit("{")
+    emit(f"    .reg .pred pa<{nbits}>, pb<{nbits}>, q<4>;")
+    emit("    .reg .b32 x, rr, a<4>;")
+    emit(f"    .reg .b64 ff, t<{depth}>, w<{nw}>, d<{nd}>;")
+    window(0)
+    preds(0, sets[0])
+    preds(1, sets[1])
+    subs()
+    setf(0)
+    jump_tree(0, sets[0], 0, nbits - 1)
+    for dd in range(kmax + 1):            # slot 0 bodies chain into slot 1's dispatch
+        emit(f"B0_{dd}:")
+        body(0, dd)
+        preds(2, sets[0])
+        setf(1)
+        jump_tree(1, sets[1], 0, nbits - 1)
+    for dd in range(kmax + 1):            # slot 1 bodies join before window B is loaded
+        emit(f"B1_{dd}:")
+        body(1, dd)
+        emit("    bra.uni HALF;")
+    emit("HALF:")
+    window(1)
+    preds(3, sets[1])
+    subs()
+    setf(2)
+    jump_tree(2, sets[0], 0, nbits - 1)
+    for dd in range(kmax + 1):
+        emit(f"B2_{dd}:")
+        body(2, dd)
+        setf(3)
+        jump_tree(3, sets[1], 0, nbits - 1)
+    for dd in range(kmax + 1):
+        emit(f"B3_{dd}:")
+        # e0, e1, f0..f3 are dead from here on: fetch the next channel's entry into them
+        emit(f"    ld.shared.v2.u32 {{{E0}, {E1}}}, [{NXT}];")
+        emit(f"    ld.shared.v4.f32 {{{F(0)}, {F(1)}, {F(2)}, {F(3)}}}, [{NXT}+16];")
+        body(3, dd)
+        emit("    bra.uni DONE;")
+    emit("DONE:")
+    emit("}")
+    asm = "\n".join(f'        "{ln}\\n"' for ln in L)
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K)] + ['"+r"(e0)', '"+r"(e1)'] +
+                     [f'"+f"(f{r})' for r in range(4)])
+    return f"""// two {nch}-chunk windows per channel (one per direction pair), deltas 0..{kmax}
+template <>
+__device__ __forceinline__ void tile_channel_step_dual<{nch}>(u64 (&acc)[4][{K}], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
+                                                          float &f2, float &f3, uint32_t row, uint32_t nxt) {{
+    asm volatile(
+{asm}
+        : {outs}
+        : "r"(row), "r"(nxt)
+        : "memory");
+}}
+"""
+
+
 print("// GENERATED by tools/gen_tile_asm.py -- do not edit.  See that script for the why.")
 print("""// One channel of one tile: window loads, differences, the four directions' accumulate bodies, and the prefetch of
 // the next channel's table entry (e0 = window byte offset, e1 = 4 x 6-bit deltas | pad phase << 24, f = fractions).
@@ -192,3 +316,9 @@ __device__ __forceinline__ void tile_channel_step(u64 (&acc)[4][8], uint32_t &e0
 """)
 for nch in (6, 8, 10):
     print(gen(nch))
+print("""template <int NCH>
+__device__ __forceinline__ void tile_channel_step_dual(u64 (&acc)[4][8], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
+                                                       float &f2, float &f3, uint32_t row, uint32_t nxt);
+""")
+for nch in (6, 7):
+    print(gen_dual(nch))
