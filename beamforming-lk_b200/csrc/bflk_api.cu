@@ -430,7 +430,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
     for (int mode = 0; mode < 3; mode++) {
         BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                        h->dir_first, h->dir_count, stage_off, 1, mode, nullptr, nullptr, n_tiles,
+                                        h->dir_first, h->dir_count, stage_off, 0, 1, mode, nullptr, nullptr, n_tiles,
                                         h->d_misc.p, h->stream));
         h->launches++;
     }
@@ -441,7 +441,9 @@ static int ensure_tiles(bflk_handle *h) {
     // direction pairs along the array's short axis still fit a 6- / 7-chunk window each: measured faster than the
     // 10-chunk single window (fewer dispatch cases, smaller code, more resident warps)
     int mode = 0;
-    if (span0 > 7 && std::min(span1, span2) <= 5) mode = span1 <= span2 ? 1 : 2;
+    const int pair_span = std::min(span1, span2), pair_mode = span1 <= span2 ? 1 : 2;
+    if (span0 > 3 && pair_span <= 3) mode = pair_mode;        // two 6-chunk windows, 16 warps
+    else if (span0 > 7 && pair_span <= 5) mode = pair_mode;   // two 7-chunk windows instead of one 10-chunk window
     if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
         const int v = atoi(env);
         if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
@@ -456,7 +458,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, h->d_tiles.reserve(entries));
     BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * sizeof(TileEntry), h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.warps, mode, h->d_tiles.p,
+                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.copy_bytes, h->tile_geom.warps, mode, h->d_tiles.p,
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -32,7 +32,7 @@ struct __align__(16) TileEntry {
 };
 
 // Tiling constants shared by the table builder (tables.cu) and the kernel (das_tile.cu).
-constexpr int kTileCC = 16;     // channels per pipeline stage
+constexpr int kTileCC = 8;      // channels per pipeline stage (a packed row holds two copies of the window data)
 // Tile tables are stored per (tile group, stage) so that one bulk copy fetches a CTA's stage; a group is
 // the `warps` direction tiles one CTA works on (one per compute warp):
 // entry(tile t, channel slot s) = tiles[((t / warps) * n_stage + s / kTileCC) * warps * kTileCC
@@ -49,7 +49,8 @@ struct TileGeometry {
     int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
     int mode = 0;        // 0: one window per tile; 1 / 2: one window per direction pair (rows of a column / columns of a row)
     int row_chunks = 0;  // logical chunks per packed row
-    int row_bytes = 0;   // padded bytes per packed row
+    int copy_bytes = 0;  // padded bytes of one copy of a packed row
+    int row_bytes = 0;   // bytes per packed row: the even-aligned copy followed by the copy shifted by one sample pair
 };
 
 // ---- lane-broadcast kernel (das_bcast.cu) -----------------------------------------------------------------
@@ -197,8 +198,9 @@ cudaError_t launch_steer_tables(const DirTrig *d_trig, int n_dir, const float *d
 cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxoff, int32_t *d_minoff, cudaStream_t st);
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, int warps, int mode,
-                               TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st);
+                               int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
+                               int mode, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan,
+                               cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
 struct GenericArgs {

@@ -56,7 +56,8 @@ struct PackArgs {
     int usable;
     int stage_off;        // first staged sample relative to a block start (even)
     int row_chunks;       // logical chunks per row
-    int row_bytes;        // padded bytes per row (multiple of 16)
+    int row_bytes;        // bytes per packed row = two padded copies (multiple of 16)
+    int copy_bytes;       // bytes of one copy
     float4 *packed;
 };
 
@@ -74,15 +75,24 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     const int64_t tA = item_start(itemA, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch;
     const int64_t tB = item_start(itemB, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch;
     const float *row = a.stream + (size_t)a.index[s] * a.row_stride;
-    float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
-    if (tA + 1 < a.row_len) A = *reinterpret_cast<const float2 *>(row + tA);
-    else if (tA < a.row_len) A.x = row[tA];
-    if (tB + 1 < a.row_len) B = *reinterpret_cast<const float2 *>(row + tB);
-    else if (tB < a.row_len) B.x = row[tB];
+    // samples 2ch, 2ch+1, 2ch+2 of both blocks (8-byte loads, zero beyond the end of the stream)
+    auto load2 = [&](int64_t t) {
+        float2 v = make_float2(0.f, 0.f);
+        if (t + 1 < a.row_len) v = *reinterpret_cast<const float2 *>(row + t);
+        else if (t < a.row_len) v.x = row[t];
+        return v;
+    };
+    const float2 A = load2(tA), A2 = load2(tA + 2), B = load2(tB), B2 = load2(tB + 2);
+    // copy 0 holds the pairs at even positions first (chunk ch = pairs 2ch, 2ch+1); copy 1 is shifted by one pair
+    // (chunk ch = pairs 2ch+1, 2ch+2) so that a window starting at an odd pair is still a 16-byte aligned LDS.128
     char *dst = reinterpret_cast<char *>(a.packed) + ((size_t)pair * a.usable + s) * a.row_bytes + 16 * padded_chunk(ch);
     *reinterpret_cast<float4 *>(dst) = make_float4(A.x, B.x, A.y, B.y);
+    *reinterpret_cast<float4 *>(dst + a.copy_bytes) = make_float4(A.y, B.y, A2.x, B2.x);
     // also fill the pad chunk that follows every fourth chunk: whole 32-byte sectors reach DRAM, no partial writes
-    if ((ch & 3) == 3 && 16 * (padded_chunk(ch) + 2) <= a.row_bytes) *reinterpret_cast<float4 *>(dst + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((ch & 3) == 3 && 16 * (padded_chunk(ch) + 2) <= a.copy_bytes) {
+        *reinterpret_cast<float4 *>(dst + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(dst + a.copy_bytes + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------------
@@ -242,14 +252,15 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     TileGeometry g;
     g.mode = mode;
     g.stage_off = (history - max_delay) & ~1;
-    g.nch = max_span <= 3 ? 6 : (mode != 0 ? 7 : (max_span <= 7 ? 8 : 10));  // two-window modes: spans up to 5
+    // chunks per lane window: 9 + span sample pairs, two per chunk (two-window modes exist for spans up to 5)
+    g.nch = max_span <= 1 && mode == 0 ? 5 : (max_span <= 3 ? 6 : (max_span <= 5 ? 7 : (max_span <= 7 ? 8 : 10)));
     // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
     // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
     // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
     // spill).  Smaller CTAs only when a small direction shard (multi-GPU) would leave the last CTA mostly idle.
     const int n_cand = 4;
     const int cand[n_cand] = {16, 12, 11, 10};
-    const double tlp[n_cand] = {g.nch == 6 ? 1.05 : 0.0, 1.0, 0.95, 0.88};
+    const double tlp[n_cand] = {g.nch <= 6 ? 1.05 : 0.0, 1.0, 0.95, 0.88};
     g.warps = 12;
     double best = 0.0;
     for (int i = 0; i < n_cand; i++) {
@@ -264,7 +275,8 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     }
     // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
     g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
-    g.row_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
+    g.copy_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
+    g.row_bytes = 2 * g.copy_bytes;  // even-aligned copy + copy shifted by one sample pair
     return g;
 }
 
@@ -303,6 +315,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.stage_off = a.geom.stage_off;
     p.row_chunks = a.geom.row_chunks;
     p.row_bytes = a.geom.row_bytes;
+    p.copy_bytes = a.geom.copy_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
     const int kWarps = a.geom.warps;
     const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * sizeof(TileEntry)) + 2 * kStages * 8;
@@ -362,7 +375,9 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         case 16: e = launch_main<NCH, 16>(ks, grid, smem, st); break;                  \
         default: e = launch_main<NCH, 12>(ks, grid, smem, st); break;                  \
     }
+            case 5: BFLK_LAUNCH(5) break;
             case 6: BFLK_LAUNCH(6) break;
+            case 7: BFLK_LAUNCH(7) break;
             case 8: BFLK_LAUNCH(8) break;
             default: BFLK_LAUNCH(10) break;
 #undef BFLK_LAUNCH

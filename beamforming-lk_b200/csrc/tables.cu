@@ -94,7 +94,8 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // tile_dirs follows the same order.  maxspan[mode] receives the largest delta of that mode.
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
-                                   int count, int stage_off, int warps, int mode, TileEntry *__restrict__ tiles,
+                                   int count, int stage_off, int copy_bytes, int warps, int mode,
+                                   TileEntry *__restrict__ tiles,
                                    int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
                                    int32_t *__restrict__ maxspan) {
     const int t = blockIdx.x;
@@ -131,9 +132,11 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
         unsigned packed = 0;
         int span = 0;
         if (mode == 0) {
-            const int base = min(min(o[0], o[1]), min(o[2], o[3])) & ~1;  // even: windows are fetched with 16-byte loads
-            const int cb = (base - stage_off) >> 1;                      // first 16-byte chunk of lane 0's window
-            e.win_off = 16u * (unsigned)(cb + (cb >> 2));                // one pad chunk after every four
+            // window = smallest offset of the tile, exactly: an odd start reads the copy shifted by one sample pair
+            const int base = min(min(o[0], o[1]), min(o[2], o[3]));
+            const int odd = (base - stage_off) & 1;
+            const int cb = (base - stage_off - odd) >> 1;                // first 16-byte chunk of lane 0's window
+            e.win_off = (unsigned)(odd * copy_bytes) + 16u * (unsigned)(cb + (cb >> 2));  // one pad chunk after every four
             packed = (unsigned)(cb & 3) << 24;
 #pragma unroll
             for (int slot = 0; slot < 4; slot++) {
@@ -145,9 +148,10 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
             e.win_off = 0;
 #pragma unroll
             for (int w = 0; w < 2; w++) {
-                const int base = min(o[2 * w], o[2 * w + 1]) & ~1;
-                const int cb = (base - stage_off) >> 1;
-                e.win_off |= (16u * (unsigned)(cb + (cb >> 2))) << (16 * w);
+                const int base = min(o[2 * w], o[2 * w + 1]);
+                const int odd = (base - stage_off) & 1;
+                const int cb = (base - stage_off - odd) >> 1;
+                e.win_off |= ((unsigned)(odd * copy_bytes) + 16u * (unsigned)(cb + (cb >> 2))) << (16 * w);
                 packed |= (unsigned)(cb & 3) << (24 + 2 * w);
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
@@ -170,12 +174,13 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 }
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
-                               int rows, int cols, int first, int count, int stage_off, int warps, int mode,
-                               TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan, cudaStream_t st) {
+                               int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
+                               int mode, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan,
+                               cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
     build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
-                                                warps, mode, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+                                                copy_bytes, warps, mode, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

@@ -314,7 +314,7 @@ template <int NCH>
 __device__ __forceinline__ void tile_channel_step(u64 (&acc)[4][8], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
                                                   float &f2, float &f3, uint32_t row, uint32_t nxt);
 """)
-for nch in (6, 8, 10):
+for nch in (5, 6, 7, 8, 10):
     print(gen(nch))
 print("""template <int NCH>
 __device__ __forceinline__ void tile_channel_step_dual(u64 (&acc)[4][8], uint32_t &e0, uint32_t &e1, float &f0, float &f1,
