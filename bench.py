@@ -341,6 +341,13 @@ def run_ours(args, c, name):
                 "frac_at_sampled_clock": (achieved_tf / (peak_tf * clocks["sm_mhz"] / max_mhz)) if achieved_tf and clocks["sm_mhz"] else None,
                 "flop_per_launch": fl, "avg_launch_ms": das_avg_s * 1e3, "launches_timed": das_n,
                 "kernel_share_of_step": das_ms / ms, "pack_share_of_step": pack_ms / ms, "traffic": None}
+        try:        # DRAM bytes per launch from the committed ncu capture of this exact command, if there is one
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(name)
+            if t and t["frames_per_step"] == B and t["kernel"] == roof["kernel"] and t["n_gpus"] == world:
+                roof["traffic"] = t["dram_bytes_per_launch"]
+                roof["traffic_source"] = t["source"]
+        except Exception:
+            pass
         roof_hbm = {"bound": "hbm", "achieved": alg_bytes / das_avg_s / 1e9 if das_n else None, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
                     "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
