@@ -28,7 +28,8 @@ SYMBOLS = [
     "bflk_default_config", "bflk_version", "bflk_create", "bflk_destroy", "bflk_last_error",
     "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_direction_range", "bflk_get_n_directions",
-    "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_batch",
+    "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
+    "bflk_power_map_batch",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
@@ -79,6 +80,7 @@ def load_library():
     L.bflk_get_tables.argtypes = [vp, vp, vp]
     L.bflk_steer_tables.argtypes = [vp, vp, vp, i32, vp, vp]
     L.bflk_power_map.argtypes = [vp, vp, vp]
+    L.bflk_power_map_i32.argtypes = [vp, vp, vp]
     L.bflk_power_map_batch.argtypes = [vp, vp, i64, i32, vp]
     L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_set_kernel.argtypes = [vp, i32]
@@ -236,6 +238,14 @@ class Beamformer:
         assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
         out = np.zeros(self.n_directions()[2], np.float32)
         self._check(self._L.bflk_power_map(self._h, _ptr(window), _ptr(out)))
+        return out
+
+    def power_map_i32(self, frames):
+        """frames [W][C] int32 wire samples (one row per time sample) -> power [count]."""
+        frames = _np(frames, np.int32)
+        assert frames.shape == (self.cfg.window_len, self.n_channels), frames.shape
+        out = np.zeros(self.n_directions()[2], np.float32)
+        self._check(self._L.bflk_power_map_i32(self._h, _ptr(frames), _ptr(out)))
         return out
 
     def power_map_batch(self, stream, n_frames):

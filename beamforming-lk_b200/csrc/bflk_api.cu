@@ -680,6 +680,27 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
     return BFLK_OK;
 }
 
+int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map_i32: set geometry and grid first");
+    if (!frames || !power_out) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_i32: null buffer");
+    const int C = h->cfg.n_channels, W = h->cfg.window_len;
+    if (C % 8) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_i32: n_channels must be a multiple of 8 (serpentine rows)");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t cnt = (size_t)W * C;
+    BFLK_CUDA(h, h->d_misc.reserve(cnt));
+    BFLK_CUDA(h, h->d_window.reserve(cnt));
+    BFLK_CUDA(h, h->d_power.reserve(h->dir_count));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_misc.p, frames, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_ingest(h->d_misc.p, W, C, h->d_window.p, h->stream));  // -> window[C][W], exposure layout
+    h->launches++;
+    int rc = power_map_dev(h, h->d_window.p, W, W, 1, h->d_power.p, h->stream);
+    if (rc) return rc;
+    BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, (size_t)h->dir_count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
 int bflk_power_map(bflk_handle *h, const float *window, float *power_out) {
     if (!h) return BFLK_ERR_INVALID;
     return bflk_power_map_batch(h, window, h->cfg.window_len, 1, power_out);

@@ -22,7 +22,7 @@
  *                                   (src/dsp/particle.cpp:37-103) as used by MISOWorker::update (miso.cpp:39-46)
  *   bflk_heatmap                    MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95)
  *   bflk_calibrate                  AWProcessingUnit::calibrate mask (aw_processing_unit.cpp:126-200)
- *   bflk_ingest_i32                 Pipeline::receive_exposure conversion (src/fpga/pipeline.cpp:260-297)
+ *   bflk_ingest_i32, bflk_power_map_i32   Pipeline::receive_exposure conversion (src/fpga/pipeline.cpp:260-297)
  */
 #ifndef BFLK_H
 #define BFLK_H
@@ -98,6 +98,10 @@ int bflk_power_map(bflk_handle *h, const float *window, float *power_out);
  * i.e. consecutive frames advance by N samples like Streams::forward().  T >= (B-1)*N + H + N + 1.
  * power_out[B][count]. */
 int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* One frame straight from the wire format: frames[W][C] int32, one row per time sample as the FPGA sends it
+ * (src/fpga/receiver.h:24-30).  The conversion of Pipeline::receive_exposure (serpentine un-flip, / 2^23,
+ * src/fpga/pipeline.cpp:260-297) runs on the device and feeds the power map without a host round trip. */
+int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out);
 /* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream);

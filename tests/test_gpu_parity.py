@@ -240,6 +240,21 @@ def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
     assert rel_err(p1, oracle.mimo_update(window, off, fr, index=np.array([17], np.int32))) <= POWER_RTOL
 
 
+def test_power_map_from_wire_samples(bf, oracle):
+    """int32 wire frames -> un-flip, / 2^23 -> power map, all on the device, against oracle ingest + MIMO update."""
+    from bflk import synth
+    c = cases.CONFIGS["cfg2"]
+    w = make(bf, c)
+    window = _synth_window(bf, c)
+    wire = synth.to_wire_i32(window)                       # [W][C] as the FPGA sends it
+    p = w.power_map_i32(wire)
+    exposure = oracle.ingest(wire)                         # quantised to 24 bits
+    off, fr = w.tables()
+    po = oracle.mimo_update(exposure, off, fr)
+    assert rel_err(p, po) <= POWER_RTOL and int(np.argmax(p)) == int(np.argmax(po))
+    assert np.array_equal(p, w.update(exposure))           # same bits as feeding the converted floats
+
+
 def test_chunked_host_batch_equals_small_batches(bf):
     """Host-buffer batches above ~64 MiB are copied and computed in overlapping chunks: same bits as separate calls."""
     from bflk import synth
