@@ -649,9 +649,12 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
     // Chunks of frames: the H2D copy of chunk k+1 (copy_stream) overlaps the kernels of chunk k (stream).
     // A chunk is ~32 MiB of new samples so PCIe and the SMs both stay busy; small batches are one chunk.
     const int64_t tail = min_stream_samples(h, 1) - N;  // samples a frame needs beyond its own N
-    int chunk_frames = (int)std::max<int64_t>(1, (32ll << 20) / ((int64_t)C * N * sizeof(float)));
-    if (chunk_frames * 2 > n_frames) chunk_frames = n_frames;
-    const int n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    int64_t chunk_bytes = 64ll << 20;  // measured on B200 / PCIe 5: 64 MiB chunks beat 32 (2-D copy rows get too short) and 96
+    if (const char *env = getenv("BFLK_CHUNK_MIB")) chunk_bytes = std::max(1, atoi(env)) * (1ll << 20);  // tuning knob
+    const int64_t frame_bytes = (int64_t)C * N * sizeof(float);
+    int n_chunks = (int)std::max<int64_t>(1, ((int64_t)n_frames * frame_bytes + chunk_bytes / 2) / chunk_bytes);
+    const int chunk_frames = (n_frames + n_chunks - 1) / n_chunks;  // even split
+    n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
     if (!h->copy_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     while ((int)h->chunk_events.size() < n_chunks) {
         cudaEvent_t e;

@@ -256,16 +256,16 @@ def test_power_map_from_wire_samples(bf, oracle):
 
 
 def test_chunked_host_batch_equals_small_batches(bf):
-    """Host-buffer batches above ~64 MiB are copied and computed in overlapping chunks: same bits as separate calls."""
+    """Host-buffer batches above ~96 MiB are copied and computed in overlapping chunks: same bits as separate calls."""
     from bflk import synth
     w = bf.MIMOWorker(cases.origins(1, 1), 8, 8, 180.0)
-    B = 1100                                               # 64 channels: 512 frames per 32 MiB chunk -> 3 chunks
+    B = 3300                                               # 64 channels x 3300 frames = 216 MB -> 3 chunks of 1100 frames
     base = synth.make_stream(synth.tile_geometry(cases.origins(1, 1)), 40 * 256 + 1024)
     stream = np.ascontiguousarray(np.tile(base[:, :40 * 256], (1, B // 40 + 2))[:, :(B - 1) * 256 + 1024])
     stream *= np.linspace(0.5, 1.5, stream.shape[1], dtype=np.float32)[None, :]      # no two frames alike
     full = w.power_map_batch(stream, B)
     assert full.shape == (B, 64) and np.all(np.isfinite(full)) and full.min() > 0
-    for b0, nb in [(0, 3), (510, 5), (1022, 4), (1097, 3)]:                          # across the chunk boundaries
+    for b0, nb in [(0, 3), (1098, 5), (2198, 4), (3297, 3)]:                         # across the chunk boundaries
         part = w.power_map_batch(np.ascontiguousarray(stream[:, b0 * 256:(b0 + nb - 1) * 256 + 1024]), nb)
         assert np.array_equal(full[b0:b0 + nb], part)
 
