@@ -240,6 +240,35 @@ def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
     assert rel_err(p1, oracle.mimo_update(window, off, fr, index=np.array([17], np.int32))) <= POWER_RTOL
 
 
+@pytest.mark.parametrize("tiles,rows,cols,fov,N,W,B,kernel", [
+    ((1, 1), 9, 9, 120.0, 256, 1024, 1, 2),        # odd grid: edge tiles have missing directions, centre cell degenerate
+    ((1, 1), 9, 9, 120.0, 256, 1024, 3, 3),
+    ((1, 1), 1, 1, 90.0, 256, 1024, 2, 0),         # a single direction
+    ((2, 1), 3, 7, 170.0, 256, 1024, 4, 0),        # very coarse grid on two arrays: automatic choice falls back
+    ((2, 1), 31, 33, 120.0, 256, 1024, 3, 2),      # odd rows and columns, two arrays, register-tiled
+    ((1, 1), 12, 10, 150.0, 512, 1536, 3, 2),      # frames of 512 samples: three overlapping 256-sample blocks
+    ((2, 1), 6, 4, 150.0, 512, 1536, 3, 3),
+    ((1, 1), 10, 12, 100.0, 1000, 2048, 2, 2),     # frame length that is no multiple of 254 or 256
+    ((2, 2), 40, 40, 180.0, 256, 1024, 7, 2),      # odd number of frames: the last block pair is half empty
+])
+def test_odd_shapes_vs_oracle(bf, oracle, tiles, rows, cols, fov, N, W, B, kernel):
+    from bflk import synth
+    org = cases.origins(*tiles)
+    w = bf.MIMOWorker(org, rows, cols, fov, frame_len=N, history=256, window_len=W)
+    w.set_kernel(kernel)
+    mask = np.array([i for i in range(64 * len(org)) if i % 7 != 3], np.int32)       # usable = 55 / 110 / 220: ragged stages
+    w.set_channel_mask(mask)
+    stream = synth.make_stream(synth.tile_geometry(org), (B - 1) * N + W)
+    p = w.power_map_batch(stream, B)
+    if kernel:
+        assert w.kernel_info()[0] == kernel
+    off, fr = w.tables()
+    for b in range(B):
+        po = oracle.mimo_update(np.ascontiguousarray(stream[:, b * N:b * N + W]), off, fr, index=mask, n=N)
+        assert rel_err(p[b], po) <= POWER_RTOL, (b, rel_err(p[b], po))
+        assert int(np.argmax(p[b])) == int(np.argmax(po))
+
+
 def test_power_map_from_wire_samples(bf, oracle):
     """int32 wire frames -> un-flip, / 2^23 -> power map, all on the device, against oracle ingest + MIMO update."""
     from bflk import synth
