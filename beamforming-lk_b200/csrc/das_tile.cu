@@ -19,6 +19,7 @@
 //    reference's exact operation triple, so the delayed sums are bit-identical to the CPU path.
 //  * epilogue: 3-tap high-pass + squares (mimo.cpp:131-135) with neighbour samples from lane +-1,
 //    warp-shuffle reduction, one store per (block, direction).
+#include <algorithm>
 #include <cstdlib>
 
 #include "bflk_internal.h"
@@ -103,7 +104,8 @@ struct KernelArgs {
     int n_tiles, usable, n_dir;
     int row_bytes;
     int n_items, blocks_per_frame, frame_len;
-    int pair0;
+    int pair0, n_pairs;          // block pairs [pair0, pair0 + n_pairs) of this launch ...
+    int pairs_per_cta;           // ... consecutive ones handled by one CTA (short channel lists: amortises the ramp-up)
     float *out;                  // power [frames][n_dir] (blocks_per_frame == 1) or partial [items][n_dir]
     float norm;
 };
@@ -121,11 +123,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages], empty[kStages]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = a.pair0 + blockIdx.y;
+    const int n_stage = (a.usable + kCC - 1) / kCC;
     const int tile0 = blockIdx.x * kWarps;
     const int my_tile = min(tile0 + warp, a.n_tiles - 1);
     const bool active = tile0 + warp < a.n_tiles;  // idle warps of the last tile group only keep the pipeline moving
-    const int n_stage = (a.usable + kCC - 1) / kCC;
+    // this CTA works on block pairs [pair_lo, pair_hi) one after the other; the staging pipeline runs straight through
+    // the pair boundaries (global stage counter gs), so the next pair's first stages load while this pair's epilogue runs
+    const int pair_lo = a.pair0 + blockIdx.y * a.pairs_per_cta;
+    const int pair_hi = min(pair_lo + a.pairs_per_cta, a.pair0 + a.n_pairs);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -136,36 +141,38 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     }
     __syncthreads();
 
-    const char *rows_g = a.packed + (size_t)pair * a.usable * a.row_bytes;
-    auto issue = [&](int st) {  // producer: one thread fills buffer st % kStages with channel chunk st
-        const int buf = st % kStages;
+    const int total_stages = n_stage * (pair_hi - pair_lo);
+    auto issue = [&](int g) {  // producer: one thread fills buffer g % kStages with global stage g = (pair, channel chunk)
+        const int pair = pair_lo + g / n_stage, st = g % n_stage;
+        const int buf = g % kStages;
         const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
         const uint32_t dst = smem + buf * stage_bytes;
         const uint32_t full = bars + 8 * buf;
         constexpr uint32_t tile_bytes = kWarps * kCC * (uint32_t)sizeof(TileEntry);
         mbar_expect_tx(full, (uint32_t)(nc * a.row_bytes) + tile_bytes);
-        bulk_g2s(dst, rows_g + (size_t)c0 * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
+        bulk_g2s(dst, a.packed + ((size_t)pair * a.usable + c0) * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
         bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC), tile_bytes, full);
     };
-    if (threadIdx.x == 0) {
-        for (int st = 0; st < min(kStages - 1, n_stage); st++) issue(st);
-    }
+    if (threadIdx.x == 0)
+        for (int g = 0; g < min(kStages - 1, total_stages); g++) issue(g);
 
+    const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
+    int gs = 0;                            // stages consumed so far by this CTA
+    for (int pair = pair_lo; pair < pair_hi; pair++) {
     u64 acc[4][kK];
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int k = 0; k < kK; k++) acc[r][k] = 0ull;
 
-    const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
-    for (int st = 0; st < n_stage; st++) {
-        const int buf = st % kStages;
+    for (int st = 0; st < n_stage; st++, gs++) {
+        const int buf = gs % kStages;
         // refill the buffer every warp left one stage ago with the chunk two stages ahead
-        if (threadIdx.x == 0 && st + kStages - 1 < n_stage) {
-            if (st >= 1) mbar_wait(bars + 8 * (kStages + (st - 1) % kStages), ((st - 1) / kStages) & 1);
-            issue(st + kStages - 1);
+        if (threadIdx.x == 0 && gs + kStages - 1 < total_stages) {
+            if (gs >= 1) mbar_wait(bars + 8 * (kStages + (gs - 1) % kStages), ((gs - 1) / kStages) & 1);
+            issue(gs + kStages - 1);
         }
-        mbar_wait(bars + 8 * buf, (st / kStages) & 1);
+        mbar_wait(bars + 8 * buf, (gs / kStages) & 1);
         const uint32_t rows_s = smem + buf * stage_bytes;
         const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * (int)sizeof(TileEntry);
         const int nc = min(kCC, a.usable - st * kCC);
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
             }
         }
     }
+    }  // block pairs of this CTA
 }
 
 // frames longer than one block: power[b][d] = (sum_q partial[b*nblk + q][d]) / norm, blocks in order
@@ -349,7 +357,11 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (hook) hook(hook_ctx, 1, false, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        dim3 grid((a.n_tiles + kWarps - 1) / kWarps, np);
+        ks.n_pairs = np;
+        // a CTA lives ~0.6 us per channel: with few channels several block pairs per CTA hide its ramp-up and epilogue
+        ks.pairs_per_cta = std::max(1, std::min(8, 512 / std::max(1, a.usable)));
+        if (const char *env = getenv("BFLK_TILE_PAIRS")) ks.pairs_per_cta = std::max(1, atoi(env));  // tuning knob
+        dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta);
         if (hook) hook(hook_ctx, 0, true, st);
         if (a.geom.mode != 0) {
             if (a.geom.nch == 6) {
