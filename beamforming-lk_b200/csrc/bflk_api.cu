@@ -430,7 +430,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
     for (int mode = 0; mode < 3; mode++) {
         BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                        h->dir_first, h->dir_count, stage_off, 0, 1, mode, nullptr, nullptr, n_tiles,
+                                        h->dir_first, h->dir_count, stage_off, 0, 1, mode, -1, nullptr, nullptr, n_tiles,
                                         h->d_misc.p, h->stream));
         h->launches++;
     }
@@ -458,7 +458,8 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, h->d_tiles.reserve(entries));
     BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * sizeof(TileEntry), h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.copy_bytes, h->tile_geom.warps, mode, h->d_tiles.p,
+                                    h->dir_first, h->dir_count, stage_off, h->tile_geom.copy_bytes, h->tile_geom.warps, mode,
+                                    2 * h->tile_geom.nch - 9, h->d_tiles.p,
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -199,8 +199,8 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
                                int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
-                               int mode, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan,
-                               cudaStream_t st);
+                               int mode, int pair_span, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles,
+                               int32_t *d_maxspan, cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
 struct GenericArgs {

@@ -94,7 +94,7 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // tile_dirs follows the same order.  maxspan[mode] receives the largest delta of that mode.
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
-                                   int count, int stage_off, int copy_bytes, int warps, int mode,
+                                   int count, int stage_off, int copy_bytes, int warps, int mode, int pair_span,
                                    TileEntry *__restrict__ tiles,
                                    int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
                                    int32_t *__restrict__ maxspan) {
@@ -145,10 +145,14 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                 packed |= (unsigned)(dlt & 63) << (6 * slot);
             }
         } else {
+            // one window per direction pair -- unless the whole tile fits a pair window for this channel: then slots 2,3
+            // reuse window A (bit 28; the kernel skips the second load + differences)
+            const int lo4 = min(min(o[0], o[1]), min(o[2], o[3])), hi4 = max(max(o[0], o[1]), max(o[2], o[3]));
+            const bool same = hi4 - lo4 <= pair_span;
             e.win_off = 0;
 #pragma unroll
             for (int w = 0; w < 2; w++) {
-                const int base = min(o[2 * w], o[2 * w + 1]);
+                const int base = same ? lo4 : min(o[2 * w], o[2 * w + 1]);
                 const int odd = (base - stage_off) & 1;
                 const int cb = (base - stage_off - odd) >> 1;
                 e.win_off |= ((unsigned)(odd * copy_bytes) + 16u * (unsigned)(cb + (cb >> 2))) << (16 * w);
@@ -160,6 +164,7 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                     packed |= (unsigned)(dlt & 63) << (6 * (2 * w + k));
                 }
             }
+            if (same) packed |= 1u << 28;
         }
         e.deltas = packed;
         e.span = span;
@@ -175,12 +180,12 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
                                int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
-                               int mode, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles, int32_t *d_maxspan,
-                               cudaStream_t st) {
+                               int mode, int pair_span, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles,
+                               int32_t *d_maxspan, cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
     build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
-                                                copy_bytes, warps, mode, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+                                                copy_bytes, warps, mode, pair_span, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

@@ -272,9 +272,14 @@ def gen_dual(nch):
         body(1, dd)
         emit("    bra.uni HALF;")
     emit("HALF:")
-    window(1)
+    # bit 28 of e1: the whole 2x2 tile fits window A for this channel -> slots 2,3 reuse its registers
+    emit(f"    and.b32 x, {E1}, {1 << 28};")
+    emit("    setp.ne.b32 q0, x, 0;")
     preds(3, sets[1])
+    emit("    @q0 bra.uni SAMEWIN;")
+    window(1)
     subs()
+    emit("SAMEWIN:")
     setf(2)
     jump_tree(2, sets[0], 0, nbits - 1)
     for dd in range(kmax + 1):
