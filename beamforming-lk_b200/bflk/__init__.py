@@ -21,7 +21,7 @@ ELEMENTS = 64         # src/geometry/antenna.h:20
 SAMPLE_RATE = 48828.0
 PROPAGATION_SPEED = 340.0
 
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_BCAST = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_BCAST, KERNEL_TILED_FMA2 = 0, 1, 2, 3, 4
 
 # every symbol include/bflk.h declares (tests check the library exports exactly these)
 SYMBOLS = [

@@ -348,7 +348,7 @@ int bflk_steer_tables(bflk_handle *h, const double *theta, const double *phi, in
 // ---- power map ---------------------------------------------------------------------------------------------
 int bflk_set_kernel(bflk_handle *h, int32_t which) {
     if (!h) return BFLK_ERR_INVALID;
-    if (which < 0 || which > 3) return h->fail(BFLK_ERR_INVALID, "bflk_set_kernel: %d", which);
+    if (which < 0 || which > 4) return h->fail(BFLK_ERR_INVALID, "bflk_set_kernel: %d", which);
     h->kernel_choice = which;
     return BFLK_OK;
 }
@@ -410,9 +410,10 @@ static int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
 }
 
 // Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.
-static int ensure_tiles(bflk_handle *h) {
-    if (h->tiles_valid) return BFLK_OK;
+static int ensure_tiles(bflk_handle *h, bool fast) {
+    if (h->tiles_valid && h->tiles_fast == fast) return BFLK_OK;
     h->tiles_valid = true;
+    h->tiles_fast = fast;
     h->tiles_usable = false;
     if (h->rows <= 0 || h->cols <= 0) return BFLK_OK;  // caller-supplied LUT: no grid structure to tile
     const int cols = h->cols;
@@ -430,7 +431,7 @@ static int ensure_tiles(bflk_handle *h) {
     BFLK_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 4 * sizeof(int32_t), h->stream));
     for (int mode = 0; mode < 3; mode++) {
         BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
-                                        h->dir_first, h->dir_count, stage_off, 0, 1, mode, -1, nullptr, nullptr, n_tiles,
+                                        h->dir_first, h->dir_count, stage_off, 0, 1, mode, -1, 0, nullptr, nullptr, n_tiles,
                                         h->d_misc.p, h->stream));
         h->launches++;
     }
@@ -448,18 +449,20 @@ static int ensure_tiles(bflk_handle *h) {
         const int v = atoi(env);
         if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
     }
+    if (fast) mode = 0;  // the two-FMA variant keeps no differences: its registers hold one window of up to 10 chunks
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[mode];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode);
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast ? 1 : 0);
     h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
     if (!h->tiles_usable) return BFLK_OK;
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
     const size_t entries = tile_table_entries(n_tiles, usable, h->tile_geom.warps);
-    BFLK_CUDA(h, h->d_tiles.reserve(entries));
-    BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * sizeof(TileEntry), h->stream));
+    const size_t ent_bytes = fast ? sizeof(TileEntryFast) : sizeof(TileEntry);
+    BFLK_CUDA(h, h->d_tiles.reserve(entries * ent_bytes));
+    BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * ent_bytes, h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
                                     h->dir_first, h->dir_count, stage_off, h->tile_geom.copy_bytes, h->tile_geom.warps, mode,
-                                    2 * h->tile_geom.nch - 9, h->d_tiles.p,
+                                    2 * h->tile_geom.nch - 9, fast ? 1 : 0, h->d_tiles.p,
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -534,11 +537,12 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
     // automatic choice: register-tiled kernel when the grid tiles (2x2 direction tiles with small offset
     // spread), else the lane-broadcast kernel (any direction list), else the generic kernel (any frame length)
     bool tiled = false;
-    if (h->kernel_choice == 0 || h->kernel_choice == 2) {
-        int rc = ensure_tiles(h);
+    if (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4) {
+        // automatic choice = the two-FMA variant (power within the 1e-4 bar); 2 asks for bit-identical delayed sums
+        int rc = ensure_tiles(h, h->kernel_choice != 2);
         if (rc) return rc;
         tiled = h->tiles_usable && !(row_stride & 1) && !((uintptr_t)stream_dev & 7);  // packed rows: 8-byte loads
-        if (h->kernel_choice == 2 && !tiled)
+        if (h->kernel_choice != 0 && !tiled)
             return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
                            h->tile_smax, das_tile_max_span());
     }
@@ -604,7 +608,7 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
         int launches = 0;
         BFLK_CUDA(h, launch_das_tile(a, h->sm_count, st, &launches, timing_hook, h));
         h->launches += launches;
-        h->kernel_last = 2;
+        h->kernel_last = h->tile_geom.fast ? 4 : 2;
     } else {
         GenericArgs a{};
         a.stream = stream_dev;

@@ -31,6 +31,17 @@ struct __align__(16) TileEntry {
     float frac[4];      // fractional delays of the 4 directions
 };
 
+// Entry of the two-FMA ("fast", tolerance mode) variant: the four pad-class byte offsets of the window ready to add to the
+// lane's row address (class m & 3 of window chunk m; no address arithmetic left in the kernel), and g = fl(1 - f).
+struct __align__(16) TileEntryFast {
+    uint32_t cls_off[4];  // byte offset of lane 0's window for chunk classes 0..3 (class k: +16 once the window crosses a pad)
+    uint32_t deltas;      // 4 x 6 bit: delta of slot r in bits [6r, 6r+6)
+    int32_t span;
+    int32_t reserved[2];
+    float frac[4];        // f
+    float comp[4];        // g = 1 - f (rounded once, here)
+};
+
 // Tiling constants shared by the table builder (tables.cu) and the kernel (das_tile.cu).
 constexpr int kTileCC = 8;      // channels per pipeline stage (a packed row holds two copies of the window data)
 // Tile tables are stored per (tile group, stage) so that one bulk copy fetches a CTA's stage; a group is
@@ -47,6 +58,7 @@ struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
     int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
     int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
+    int fast = 0;        // 1: two-FMA form (TileEntryFast tables, one window per tile)
     int mode = 0;        // 0: one window per tile; 1 / 2: one window per direction pair (rows of a column / columns of a row)
     int row_chunks = 0;  // logical chunks per packed row
     int copy_bytes = 0;  // padded bytes of one copy of a packed row
@@ -137,9 +149,10 @@ struct bflk_handle {
     // register-tiled kernel tables (built lazily for the current grid / mask / range)
     bool tiles_valid = false;
     bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
+    bool tiles_fast = false;     // the tables were built for the two-FMA variant
     int32_t n_tiles = 0;
     int32_t tile_smax = 0;       // compiled window slack the tables need
-    bflk::DevBuf<bflk::TileEntry> d_tiles;  // tile_table_entries(n_tiles, usable), layout above
+    bflk::DevBuf<char> d_tiles;             // tile_table_entries(n_tiles, usable) TileEntry / TileEntryFast, layout above
     bflk::DevBuf<int32_t> d_tile_dirs;      // [n_tiles][4] local direction index (or -1)
     bflk::TileGeometry tile_geom;
     bflk::DevBuf<char> d_packed;            // pair-interleaved staging rows of the current batch
@@ -199,7 +212,7 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 // tile tables for directions [first, first+count) of a rows x cols grid, 2x2 direction tiles.
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
                                int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
-                               int mode, int pair_span, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles,
+                               int mode, int pair_span, int fast, void *d_tiles, int32_t *d_tile_dirs, int n_tiles,
                                int32_t *d_maxspan, cudaStream_t st);
 
 // ---- das_generic.cu ---------------------------------------------------------------------------------
@@ -229,7 +242,7 @@ struct TileArgs {
     int n_frames;
     int frame_len;
     int frame_stride;
-    const TileEntry *tiles;      // tile_table_entries() entries, grouped per (tile group, stage)
+    const void *tiles;           // tile_table_entries() entries (TileEntry, or TileEntryFast when geom.fast), grouped per (tile group, stage)
     const int32_t *tile_dirs;    // [n_tiles][4]
     int n_tiles;
     int usable;
@@ -246,7 +259,7 @@ typedef void (*TileLaunchHook)(void *ctx, int kind, bool begin, cudaStream_t st)
 cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
                             void *hook_ctx = nullptr);
 int das_tile_max_span();
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0);
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0, int fast = 0);
 size_t das_tile_packed_bytes(const TileArgs &a);
 
 // ---- das_bcast.cu -----------------------------------------------------------------------------------

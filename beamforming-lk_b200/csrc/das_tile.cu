@@ -33,6 +33,7 @@ constexpr int kCC = kTileCC;         // channels per pipeline stage
 constexpr int kStages = 3;
 constexpr int kBlock = 256;          // output samples per block
 constexpr int kK = 8;                // sample pairs per lane
+constexpr int kFastMaxNch16 = 10;    // largest window of the two-FMA variant that still runs 16 warps per CTA
 
 // chunk (16 B = 2 sample pairs) c of a row lives at padded chunk c + (c >> 2)
 __host__ __device__ __forceinline__ int padded_chunk(int c) { return c + (c >> 2); }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
 // ---- main kernel ---------------------------------------------------------------------------------------------
 struct KernelArgs {
     const char *packed;          // [pair][usable][row_bytes]
-    const TileEntry *tiles;      // grouped per (tile group, stage), see tile_table_entries()
+    const char *tiles;           // TileEntry / TileEntryFast, grouped per (tile group, stage), see tile_table_entries()
     const int32_t *tile_dirs;    // [n_tiles][4]
     int n_tiles, usable, n_dir;
     int row_bytes;
@@ -111,14 +112,18 @@ struct KernelArgs {
 };
 
 #include "das_tile_asm.inc"
+#include "das_tile_fast_asm.inc"
 
 // DUAL: two NCH-chunk windows per channel, one per direction pair (tile tables built with mode 1 / 2), NCH 6 or 7
-template <int NCH, int kWarps, bool DUAL = false>
+// FAST: two-FMA form acc += g s[i+1]; acc += f s[i] (TileEntryFast tables; power within 1e-4 of the reference instead of
+//       bit-identical delayed sums) -- 16 FFMA2 per (direction, channel) and no other FP instruction
+template <int NCH, int kWarps, bool DUAL = false, bool FAST = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * 32 } then barriers
+    constexpr int kEnt = FAST ? (int)sizeof(TileEntryFast) : (int)sizeof(TileEntry);
+    // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * kEnt } then barriers
     const int stage_rows = kCC * a.row_bytes;
-    const int stage_bytes = stage_rows + kWarps * kCC * (int)sizeof(TileEntry);
+    const int stage_bytes = stage_rows + kWarps * kCC * kEnt;
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages], empty[kStages]
 
@@ -148,10 +153,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
         const uint32_t dst = smem + buf * stage_bytes;
         const uint32_t full = bars + 8 * buf;
-        constexpr uint32_t tile_bytes = kWarps * kCC * (uint32_t)sizeof(TileEntry);
+        constexpr uint32_t tile_bytes = kWarps * kCC * (uint32_t)kEnt;
         mbar_expect_tx(full, (uint32_t)(nc * a.row_bytes) + tile_bytes);
         bulk_g2s(dst, a.packed + ((size_t)pair * a.usable + c0) * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
-        bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC), tile_bytes, full);
+        bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC) * kEnt, tile_bytes, full);
     };
     if (threadIdx.x == 0)
         for (int g = 0; g < min(kStages - 1, total_stages); g++) issue(g);
@@ -174,8 +179,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         }
         mbar_wait(bars + 8 * buf, (gs / kStages) & 1);
         const uint32_t rows_s = smem + buf * stage_bytes;
-        const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * (int)sizeof(TileEntry);
+        const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * kEnt;
         const int nc = min(kCC, a.usable - st * kCC);
+        if constexpr (FAST) {
+            // the whole stage in one asm block: entry prefetch, window loads, four dispatched bodies, loop
+            if (active) tile_stage_fast<NCH>(acc, tiles_s, rows_s + lane_off, (uint32_t)nc, (uint32_t)a.row_bytes);
+        } else
         if (active) {
             uint32_t e0, e1;
             float f0, f1, f2, f3;
@@ -256,19 +265,21 @@ __global__ void finalize_kernel(const float *__restrict__ partial, int n_frames,
 // ---- host side ---------------------------------------------------------------------------------------------------
 int das_tile_max_span() { return 11; }
 
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode) {
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast) {
     TileGeometry g;
     g.mode = mode;
+    g.fast = fast;
     g.stage_off = (history - max_delay) & ~1;
     // chunks per lane window: 9 + span sample pairs, two per chunk (two-window modes exist for spans up to 5)
     g.nch = max_span <= 1 && mode == 0 ? 5 : (max_span <= 3 ? 6 : (max_span <= 5 ? 7 : (max_span <= 7 ? 8 : 10)));
+    if (fast) g.nch = std::max(5, (9 + max_span + 1) / 2);
     // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
     // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
     // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
     // spill).  Smaller CTAs only when a small direction shard (multi-GPU) would leave the last CTA mostly idle.
     const int n_cand = 4;
     const int cand[n_cand] = {16, 12, 11, 10};
-    const double tlp[n_cand] = {g.nch <= 6 ? 1.05 : 0.0, 1.0, 0.95, 0.88};
+    const double tlp[n_cand] = {g.nch <= 6 || (fast && g.nch <= kFastMaxNch16) ? 1.05 : 0.0, 1.0, 0.95, 0.88};
     g.warps = 12;
     double best = 0.0;
     for (int i = 0; i < n_cand; i++) {
@@ -288,11 +299,11 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     return g;
 }
 
-template <int NCH, int WARPS, bool DUAL = false>
+template <int NCH, int WARPS, bool DUAL = false, bool FAST = false>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    das_tile_kernel<NCH, WARPS, DUAL><<<grid, WARPS * 32, smem, st>>>(k);
+    das_tile_kernel<NCH, WARPS, DUAL, FAST><<<grid, WARPS * 32, smem, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -326,12 +337,14 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.copy_bytes = a.geom.copy_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
     const int kWarps = a.geom.warps;
-    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * sizeof(TileEntry)) + 2 * kStages * 8;
+    const size_t ent_bytes = a.geom.fast ? sizeof(TileEntryFast) : sizeof(TileEntry);
+    // + 64: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
+    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * kStages * 8 + 64;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 
     KernelArgs k{};
     k.packed = reinterpret_cast<const char *>(a.packed);
-    k.tiles = a.tiles;
+    k.tiles = static_cast<const char *>(a.tiles);
     k.tile_dirs = a.tile_dirs;
     k.n_tiles = a.n_tiles;
     k.usable = a.usable;
@@ -363,7 +376,24 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (const char *env = getenv("BFLK_TILE_PAIRS")) ks.pairs_per_cta = std::max(1, atoi(env));  // tuning knob
         dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta);
         if (hook) hook(hook_ctx, 0, true, st);
-        if (a.geom.mode != 0) {
+        if (a.geom.fast) {
+            switch (a.geom.nch) {
+#define BFLK_LAUNCH_FAST(NCH)                                                          \
+    switch (a.geom.warps) {                                                            \
+        case 10: e = launch_main<NCH, 10, false, true>(ks, grid, smem, st); break;     \
+        case 11: e = launch_main<NCH, 11, false, true>(ks, grid, smem, st); break;     \
+        case 16: e = launch_main<NCH, 16, false, true>(ks, grid, smem, st); break;     \
+        default: e = launch_main<NCH, 12, false, true>(ks, grid, smem, st); break;     \
+    }
+                case 5: BFLK_LAUNCH_FAST(5) break;
+                case 6: BFLK_LAUNCH_FAST(6) break;
+                case 7: BFLK_LAUNCH_FAST(7) break;
+                case 8: BFLK_LAUNCH_FAST(8) break;
+                case 9: BFLK_LAUNCH_FAST(9) break;
+                default: BFLK_LAUNCH_FAST(10) break;
+#undef BFLK_LAUNCH_FAST
+            }
+        } else if (a.geom.mode != 0) {
             if (a.geom.nch == 6) {
                 switch (a.geom.warps) {
                     case 10: e = launch_main<6, 10, true>(ks, grid, smem, st); break;

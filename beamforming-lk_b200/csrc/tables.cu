@@ -95,11 +95,13 @@ cudaError_t launch_offset_range(const int32_t *d_off, size_t n, int32_t *d_maxof
 __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float *__restrict__ frac, int C,
                                    const int32_t *__restrict__ index, int usable, int rows, int cols, int first,
                                    int count, int stage_off, int copy_bytes, int warps, int mode, int pair_span,
-                                   TileEntry *__restrict__ tiles,
+                                   int fast, void *__restrict__ tiles_raw,
                                    int32_t *__restrict__ tile_dirs, int n_tiles, int tile_cols, int row0,
                                    int32_t *__restrict__ maxspan) {
     const int t = blockIdx.x;
     if (t >= n_tiles) return;
+    TileEntry *tiles = fast ? nullptr : static_cast<TileEntry *>(tiles_raw);
+    TileEntryFast *tiles_fast = fast ? static_cast<TileEntryFast *>(tiles_raw) : nullptr;
     const int tr = t / tile_cols, tc = t % tile_cols;
     int dirs[4];
 #pragma unroll
@@ -170,8 +172,23 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
         e.span = span;
         e.reserved = 0;
         const int n_stage = (usable + kTileCC - 1) / kTileCC;
-        if (tiles)
-            tiles[((size_t)(t / warps) * n_stage + s / kTileCC) * (warps * kTileCC) + (t % warps) * kTileCC + s % kTileCC] = e;
+        const size_t slot = ((size_t)(t / warps) * n_stage + s / kTileCC) * (warps * kTileCC) + (t % warps) * kTileCC + s % kTileCC;
+        if (tiles) tiles[slot] = e;
+        if (tiles_fast) {  // mode 0 only
+            TileEntryFast q;
+            const unsigned r = (packed >> 24) & 3;
+#pragma unroll
+            for (int k = 0; k < 4; k++) q.cls_off[k] = e.win_off + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
+            q.deltas = packed & 0xffffffu;
+            q.span = span;
+            q.reserved[0] = q.reserved[1] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                q.frac[k] = e.frac[k];
+                q.comp[k] = __fsub_rn(1.0f, e.frac[k]);
+            }
+            tiles_fast[slot] = q;
+        }
         span_max = max(span_max, span);
     }
     for (int o = 16; o > 0; o >>= 1) span_max = max(span_max, __shfl_xor_sync(0xffffffffu, span_max, o));
@@ -180,12 +197,12 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 
 cudaError_t launch_build_tiles(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
                                int rows, int cols, int first, int count, int stage_off, int copy_bytes, int warps,
-                               int mode, int pair_span, TileEntry *d_tiles, int32_t *d_tile_dirs, int n_tiles,
+                               int mode, int pair_span, int fast, void *d_tiles, int32_t *d_tile_dirs, int n_tiles,
                                int32_t *d_maxspan, cudaStream_t st) {
     const int row0 = (first / cols) & ~1;
     const int tile_cols = (cols + 1) / 2;
     build_tiles_kernel<<<n_tiles, 128, 0, st>>>(d_off, d_frac, C, d_index, usable, rows, cols, first, count, stage_off,
-                                                copy_bytes, warps, mode, pair_span, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
+                                                copy_bytes, warps, mode, pair_span, fast, d_tiles, d_tile_dirs, n_tiles, tile_cols, row0, d_maxspan);
     return cudaGetLastError();
 }
 

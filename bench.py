@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=list(cases.CONFIGS))
     ap.add_argument("--frames", type=int, default=0, help="frames per step (default: sized so the input exceeds L2)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 register-tiled, 3 lane-broadcast")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 register-tiled (bit-identical sums), 3 lane-broadcast, 4 register-tiled two-FMA form")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -335,7 +335,7 @@ def run_ours(args, c, name):
         das_avg_s = das_ms / 1e3 / max(1, das_n)
         achieved_tf = fl / das_avg_s / 1e12 if das_n else None
         alg_bytes = 4 * C * T + 4 * B * count
-        roof = {"bound": "fp32", "kernel": {1: "das_generic", 2: "das_tile", 3: "das_bcast"}.get(kinfo[0], "?"), "achieved": achieved_tf,
+        roof = {"bound": "fp32", "kernel": {1: "das_generic", 2: "das_tile", 3: "das_bcast", 4: "das_tile_fma2"}.get(kinfo[0], "?"), "achieved": achieved_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if achieved_tf else None,
                 "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz {max_mhz:.0f} ({pk_kind} MEASURED_PEAKS.json clock)",
                 "frac_at_sampled_clock": (achieved_tf / (peak_tf * clocks["sm_mhz"] / max_mhz)) if achieved_tf and clocks["sm_mhz"] else None,

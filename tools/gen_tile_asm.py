@@ -19,6 +19,7 @@ Rejected variants, kept behind flags: BFLK_GEN_VOTE=1 (vote-uniform predicates, 
 (brx.idx jump table, -9 .. -22 %), BFLK_GEN_CHAIN=0 (join after every direction).
 
 usage: python tools/gen_tile_asm.py > beamforming-lk_b200/csrc/das_tile_asm.inc
+       python tools/gen_tile_asm.py --fast > beamforming-lk_b200/csrc/das_tile_fast_asm.inc
 """
 import os
 
@@ -311,6 +312,116 @@ __device__ __forceinline__ void tile_channel_step_dual<{nch}>(u64 (&acc)[4][{K}]
 }}
 """
 
+
+
+def gen_fast(nch):
+    """Two-FMA form (tolerance mode): acc += g * s[i+1]; acc += f * s[i], g = fl(1 - f) from the table.  No differences,
+    no temporaries: 16 FFMA2 per (direction, channel) and nothing else on the FP pipe.  One asm block runs ALL channels
+    of a pipeline stage (the loop branch is the tail of the last direction's body, so there is no join point per
+    channel); the 64-byte table entry carries the four pad-class window offsets ready to add to the lane's row address.
+    operands: acc[4][8] "+l" 0..31, ent 32 "+r" (shared address of the current entry), row 33 "+r" (lane's row start),
+    cnt 34 "+r" (channels left), rb 35 "r" (bytes per packed row)."""
+    nw = 2 * nch
+    kmax = 2 * nch - 9
+    nbits = max(1, kmax.bit_length())
+    ENT, ROWR, CNT, RB = "%32", "%33", "%34", "%35"
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        for k in range(K):
+            emit(f"    fma.rn.f32x2 {A(r, k)}, gg{r}, w{D + k + 1}, {A(r, k)};")
+        for k in range(K):
+            emit(f"    fma.rn.f32x2 {A(r, k)}, ff{r}, w{D + k}, {A(r, k)};")
+
+    def preds(r):
+        for b in range(nbits):
+            emit(f"    and.b32 x, dl, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 p{b}, x, 0;")
+
+    uid = [0]
+
+    def jump_tree(r, d0, bit):
+        if bit < 0:
+            emit(f"    bra.uni B{r}_{d0};")
+            return
+        hi = d0 + (1 << bit)
+        if hi > kmax:
+            jump_tree(r, d0, bit - 1)
+            return
+        uid[0] += 1
+        lab = f"N{uid[0]}"
+        emit(f"    @p{bit} bra.uni {lab};")
+        jump_tree(r, d0, bit - 1)
+        emit(f"{lab}:")
+        jump_tree(r, hi, bit - 1)
+
+    emit("{")
+    emit(f"    .reg .pred p<{nbits}>, ploop;")
+    emit("    .reg .b32 x, dl, o<4>;")
+    emit("    .reg .f32 f<4>, g<4>;")
+    emit(f"    .reg .b64 ff<4>, gg<4>, w<{nw}>;")
+    emit(f"    ld.shared.v4.u32 {{o0, o1, o2, o3}}, [{ENT}];")
+    emit(f"    ld.shared.u32 dl, [{ENT}+16];")
+    emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+32];")
+    emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+48];")
+    emit("TOP:")
+    for c in range(4):
+        emit(f"    add.u32 o{c}, o{c}, {ROWR};")
+    for m in range(nch):
+        emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [o{m & 3}+{16 * (m + (m >> 2))}];")
+    emit(f"    add.u32 {ENT}, {ENT}, 64;")
+    emit(f"    add.u32 {ROWR}, {ROWR}, {RB};")
+    emit(f"    add.u32 {CNT}, {CNT}, -1;")
+    emit(f"    setp.ne.u32 ploop, {CNT}, 0;")
+    preds(0)
+    for r in range(4):
+        emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
+        emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
+    jump_tree(0, 0, nbits - 1)
+    for r in range(4):
+        for dd in range(kmax + 1):
+            emit(f"B{r}_{dd}:")
+            if r < 3:
+                preds(r + 1)
+                body(r, dd)
+                jump_tree(r + 1, 0, nbits - 1)
+            else:
+                # the next channel's entry: offsets + deltas now (dead since the window loads / predicates), fractions
+                # after the last FFMA2 that reads them (the read past a stage's last entry is never used)
+                emit(f"    ld.shared.v4.u32 {{o0, o1, o2, o3}}, [{ENT}];")
+                emit(f"    ld.shared.u32 dl, [{ENT}+16];")
+                body(r, dd)
+                emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+32];")
+                emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+48];")
+                emit("    @ploop bra.uni TOP;")
+                emit("    bra.uni DONE;")
+    emit("DONE:")
+    emit("}")
+    asm = "\n".join(f'        "{ln}\\n"' for ln in L)
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K)] + ['"+r"(ent)', '"+r"(row)', '"+r"(cnt)'])
+    return f"""// NCH = {nch}: window of {nw} sample pairs, deltas 0..{kmax}
+template <>
+__device__ __forceinline__ void tile_stage_fast<{nch}>(u64 (&acc)[4][{K}], uint32_t ent, uint32_t row, uint32_t cnt, uint32_t rb) {{
+    asm volatile(
+{asm}
+        : {outs}
+        : "r"(rb)
+        : "memory");
+}}
+"""
+
+
+import sys
+if "--fast" in sys.argv:
+    print("// GENERATED by tools/gen_tile_asm.py --fast -- do not edit.  See that script for the why.")
+    print("""// All channels of one pipeline stage for one tile, two-FMA form (tolerance mode).
+template <int NCH>
+__device__ __forceinline__ void tile_stage_fast(u64 (&acc)[4][8], uint32_t ent, uint32_t row, uint32_t cnt, uint32_t rb);
+""")
+    for nch in (5, 6, 7, 8, 9, 10):
+        print(gen_fast(nch))
+    sys.exit(0)
 
 print("// GENERATED by tools/gen_tile_asm.py -- do not edit.  See that script for the why.")
 print("""// One channel of one tile: window loads, differences, the four directions' accumulate bodies, and the prefetch of
