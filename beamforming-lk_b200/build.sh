@@ -8,7 +8,7 @@ mkdir -p build
 objs=()
 for f in csrc/bflk_api.cu csrc/tables.cu csrc/das_generic.cu csrc/das_tile.cu csrc/das_bcast.cu csrc/post.cu; do
   o=build/$(basename "${f%.cu}").o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/bflk_internal.h -nt "$o" ] || [ csrc/das_common.cuh -nt "$o" ] || [ csrc/das_tile_asm.inc -nt "$o" ] || [ ../include/bflk.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/bflk_internal.h -nt "$o" ] || [ csrc/das_common.cuh -nt "$o" ] || [ csrc/das_tile_asm.inc -nt "$o" ] || [ csrc/das_tile_fast_asm.inc -nt "$o" ] || [ ../include/bflk.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi
   objs+=("$o")

@@ -449,7 +449,16 @@ static int ensure_tiles(bflk_handle *h, bool fast) {
         const int v = atoi(env);
         if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
     }
-    if (fast) mode = 0;  // the two-FMA variant keeps no differences: its registers hold one window of up to 10 chunks
+    if (fast) {
+        // the two-FMA variant keeps no differences, so one window of up to 10 chunks fits its registers; two 6- / 7-chunk
+        // windows (small dispatch trees, small code) are still faster once the 2x2 spread needs more than 7 chunks
+        mode = 0;
+        if (span0 > 5 && pair_span <= 5) mode = pair_mode;
+        if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
+            const int v = atoi(env);
+            if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
+        }
+    }
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[mode];
     h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast ? 1 : 0);
@@ -457,7 +466,7 @@ static int ensure_tiles(bflk_handle *h, bool fast) {
     if (!h->tiles_usable) return BFLK_OK;
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
     const size_t entries = tile_table_entries(n_tiles, usable, h->tile_geom.warps);
-    const size_t ent_bytes = fast ? sizeof(TileEntryFast) : sizeof(TileEntry);
+    const size_t ent_bytes = das_tile_entry_bytes(h->tile_geom);
     BFLK_CUDA(h, h->d_tiles.reserve(entries * ent_bytes));
     BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * ent_bytes, h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,

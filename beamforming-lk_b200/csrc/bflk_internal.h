@@ -34,12 +34,22 @@ struct __align__(16) TileEntry {
 // Entry of the two-FMA ("fast", tolerance mode) variant: the four pad-class byte offsets of the window ready to add to the
 // lane's row address (class m & 3 of window chunk m; no address arithmetic left in the kernel), and g = fl(1 - f).
 struct __align__(16) TileEntryFast {
-    uint32_t cls_off[4];  // byte offset of lane 0's window for chunk classes 0..3 (class k: +16 once the window crosses a pad)
+    uint32_t cls_off[4];  // byte offset of lane 0's window inside the STAGE (row offset (s % kTileCC) * row_bytes included) for chunk classes 0..3
     uint32_t deltas;      // 4 x 6 bit: delta of slot r in bits [6r, 6r+6)
     int32_t span;
     int32_t reserved[2];
     float frac[4];        // f
     float comp[4];        // g = 1 - f (rounded once, here)
+};
+
+// Two-window flavour of the same (modes 1 / 2): class offsets of window A (slots 0,1) and window B (slots 2,3); bit 28 of
+// deltas = the whole tile fits window A for this channel (window B is not loaded).
+struct __align__(16) TileEntryFastDual {
+    uint32_t cls_a[4], cls_b[4];
+    float frac[4], comp[4];
+    uint32_t deltas;
+    int32_t span;
+    int32_t reserved[2];
 };
 
 // Tiling constants shared by the table builder (tables.cu) and the kernel (das_tile.cu).
@@ -261,6 +271,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
 int das_tile_max_span();
 TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0, int fast = 0);
 size_t das_tile_packed_bytes(const TileArgs &a);
+size_t das_tile_entry_bytes(const TileGeometry &g);
 
 // ---- das_bcast.cu -----------------------------------------------------------------------------------
 struct BcastArgs {

@@ -120,7 +120,7 @@ struct KernelArgs {
 template <int NCH, int kWarps, bool DUAL = false, bool FAST = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int kEnt = FAST ? (int)sizeof(TileEntryFast) : (int)sizeof(TileEntry);
+    constexpr int kEnt = FAST ? (DUAL ? (int)sizeof(TileEntryFastDual) : (int)sizeof(TileEntryFast)) : (int)sizeof(TileEntry);
     // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * kEnt } then barriers
     const int stage_rows = kCC * a.row_bytes;
     const int stage_bytes = stage_rows + kWarps * kCC * kEnt;
@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         const int nc = min(kCC, a.usable - st * kCC);
         if constexpr (FAST) {
             // the whole stage in one asm block: entry prefetch, window loads, four dispatched bodies, loop
-            if (active) tile_stage_fast<NCH>(acc, tiles_s, rows_s + lane_off, (uint32_t)nc, (uint32_t)a.row_bytes);
+            if (active) {
+                // (the entries' window offsets include the row's offset inside the stage)
+                if constexpr (DUAL) tile_stage_fast_dual<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
+                else tile_stage_fast<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
+            }
         } else
         if (active) {
             uint32_t e0, e1;
@@ -272,7 +276,10 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     g.stage_off = (history - max_delay) & ~1;
     // chunks per lane window: 9 + span sample pairs, two per chunk (two-window modes exist for spans up to 5)
     g.nch = max_span <= 1 && mode == 0 ? 5 : (max_span <= 3 ? 6 : (max_span <= 5 ? 7 : (max_span <= 7 ? 8 : 10)));
-    if (fast) g.nch = std::max(5, (9 + max_span + 1) / 2);
+    if (fast) {
+        g.nch = std::max(mode ? 6 : 5, (9 + max_span + 1) / 2);
+        if (const char *env = getenv("BFLK_TILE_NCH")) g.nch = std::min(mode ? 7 : 10, std::max(g.nch, atoi(env)));  // tuning knob
+    }
     // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
     // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
     // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
@@ -297,6 +304,10 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     g.copy_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
     g.row_bytes = 2 * g.copy_bytes;  // even-aligned copy + copy shifted by one sample pair
     return g;
+}
+
+size_t das_tile_entry_bytes(const TileGeometry &g) {
+    return g.fast ? (g.mode ? sizeof(TileEntryFastDual) : sizeof(TileEntryFast)) : sizeof(TileEntry);
 }
 
 template <int NCH, int WARPS, bool DUAL = false, bool FAST = false>
@@ -337,9 +348,9 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.copy_bytes = a.geom.copy_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
     const int kWarps = a.geom.warps;
-    const size_t ent_bytes = a.geom.fast ? sizeof(TileEntryFast) : sizeof(TileEntry);
-    // + 64: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
-    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * kStages * 8 + 64;
+    const size_t ent_bytes = das_tile_entry_bytes(a.geom);
+    // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
+    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * kStages * 8 + 96;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 
     KernelArgs k{};
@@ -376,7 +387,23 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (const char *env = getenv("BFLK_TILE_PAIRS")) ks.pairs_per_cta = std::max(1, atoi(env));  // tuning knob
         dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta);
         if (hook) hook(hook_ctx, 0, true, st);
-        if (a.geom.fast) {
+        if (a.geom.fast && a.geom.mode != 0) {
+            if (a.geom.nch == 6) {
+                switch (a.geom.warps) {
+                    case 10: e = launch_main<6, 10, true, true>(ks, grid, smem, st); break;
+                    case 11: e = launch_main<6, 11, true, true>(ks, grid, smem, st); break;
+                    case 12: e = launch_main<6, 12, true, true>(ks, grid, smem, st); break;
+                    default: e = launch_main<6, 16, true, true>(ks, grid, smem, st); break;
+                }
+            } else {
+                switch (a.geom.warps) {
+                    case 10: e = launch_main<7, 10, true, true>(ks, grid, smem, st); break;
+                    case 11: e = launch_main<7, 11, true, true>(ks, grid, smem, st); break;
+                    case 12: e = launch_main<7, 12, true, true>(ks, grid, smem, st); break;
+                    default: e = launch_main<7, 16, true, true>(ks, grid, smem, st); break;
+                }
+            }
+        } else if (a.geom.fast) {
             switch (a.geom.nch) {
 #define BFLK_LAUNCH_FAST(NCH)                                                          \
     switch (a.geom.warps) {                                                            \

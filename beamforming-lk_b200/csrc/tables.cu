@@ -101,7 +101,8 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
     const int t = blockIdx.x;
     if (t >= n_tiles) return;
     TileEntry *tiles = fast ? nullptr : static_cast<TileEntry *>(tiles_raw);
-    TileEntryFast *tiles_fast = fast ? static_cast<TileEntryFast *>(tiles_raw) : nullptr;
+    TileEntryFast *tiles_fast = fast && mode == 0 ? static_cast<TileEntryFast *>(tiles_raw) : nullptr;
+    TileEntryFastDual *tiles_fast2 = fast && mode != 0 ? static_cast<TileEntryFastDual *>(tiles_raw) : nullptr;
     const int tr = t / tile_cols, tc = t % tile_cols;
     int dirs[4];
 #pragma unroll
@@ -178,7 +179,8 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
             TileEntryFast q;
             const unsigned r = (packed >> 24) & 3;
 #pragma unroll
-            for (int k = 0; k < 4; k++) q.cls_off[k] = e.win_off + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
+            for (int k = 0; k < 4; k++)
+                q.cls_off[k] = (unsigned)(s % kTileCC) * 2u * (unsigned)copy_bytes + e.win_off + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
             q.deltas = packed & 0xffffffu;
             q.span = span;
             q.reserved[0] = q.reserved[1] = 0;
@@ -188,6 +190,25 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                 q.comp[k] = __fsub_rn(1.0f, e.frac[k]);
             }
             tiles_fast[slot] = q;
+        }
+        if (tiles_fast2) {  // modes 1 / 2
+            TileEntryFastDual q;
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const unsigned wo = (e.win_off >> (16 * w)) & 0xffffu, r = (packed >> (24 + 2 * w)) & 3;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    (w ? q.cls_b : q.cls_a)[k] = (unsigned)(s % kTileCC) * 2u * (unsigned)copy_bytes + wo + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
+            }
+            q.deltas = packed & 0x10ffffffu;
+            q.span = span;
+            q.reserved[0] = q.reserved[1] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                q.frac[k] = e.frac[k];
+                q.comp[k] = __fsub_rn(1.0f, e.frac[k]);
+            }
+            tiles_fast2[slot] = q;
         }
         span_max = max(span_max, span);
     }

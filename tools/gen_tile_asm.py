@@ -314,17 +314,30 @@ __device__ __forceinline__ void tile_channel_step_dual<{nch}>(u64 (&acc)[4][{K}]
 
 
 
-def gen_fast(nch):
+def gen_fast(nch, dual=False):
     """Two-FMA form (tolerance mode): acc += g * s[i+1]; acc += f * s[i], g = fl(1 - f) from the table.  No differences,
-    no temporaries: 16 FFMA2 per (direction, channel) and nothing else on the FP pipe.  One asm block runs ALL channels
-    of a pipeline stage (the loop branch is the tail of the last direction's body, so there is no join point per
-    channel); the 64-byte table entry carries the four pad-class window offsets ready to add to the lane's row address.
-    operands: acc[4][8] "+l" 0..31, ent 32 "+r" (shared address of the current entry), row 33 "+r" (lane's row start),
-    cnt 34 "+r" (channels left), rb 35 "r" (bytes per packed row)."""
+    no temporaries: 16 FFMA2 per (direction, channel) and nothing else on the FP pipe.
+
+    One asm block runs ALL channels of a pipeline stage; there is no join point per channel:
+      * one chain per delta value: B0_d, B1_d, B2_d, B3_d.  The dispatch at the end of a body tests the next direction's
+        delta bits with the polarity of its OWN delta, so "same delta as the previous direction" needs no taken branch;
+        any other delta leaves through one taken branch into a shared subtree;
+      * the last direction's body advances the entry pointer, fetches the next channel's table entry, forms the window
+        addresses (the entry carries the four pad-class offsets, row offset inside the stage included, ready to add to
+        the lane's base) and the first direction's predicates, then loops: the next iteration starts with its window
+        loads.  No register that an in-flight LDS still reads as its address is written (ncu: that WAR wait on the
+        short scoreboard was 15 % of all stall samples in the first version).
+    dual: two windows per channel (slots 0,1 -> window A, slots 2,3 -> window B, through the same registers); bit 28 of
+    the delta word says the whole tile fits window A for this channel (window B is not loaded).
+    operands: acc[4][8] "+l" 0..31, ent 32 "+r" (shared address of the current entry), row 33 "r" (lane's base inside
+    the stage's rows), end 34 "r" (shared address one past the stage's last entry of this warp).
+    entry (single, 64 B): o[4] | dl, -, -, - | f[4] | g[4];   (dual, 80 B): oA[4] | oB[4] | f[4] | g[4] | dl, -, -, -"""
     nw = 2 * nch
     kmax = 2 * nch - 9
     nbits = max(1, kmax.bit_length())
-    ENT, ROWR, CNT, RB = "%32", "%33", "%34", "%35"
+    ENT, ROWR, END = "%32", "%33", "%34"
+    esz = 80 if dual else 64
+    o_dl, o_f, o_g = (64, 32, 48) if dual else (16, 32, 48)
     L = []
     emit = L.append
 
@@ -339,74 +352,122 @@ def gen_fast(nch):
             emit(f"    and.b32 x, dl, {1 << (6 * r + b)};")
             emit(f"    setp.ne.b32 p{b}, x, 0;")
 
-    uid = [0]
+    first_window = [True]
 
-    def jump_tree(r, d0, bit):
+    def window(o):
+        if os.environ.get("BFLK_GEN_EXP") == "nolds" and not first_window[0]:
+            return      # timing experiment only (wrong results): how much do the window loads cost?
+        for m in range(nch):
+            emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [{o}{m & 3}+{16 * (m + (m >> 2))}];")
+
+    def load_entry_head():
+        emit(f"    ld.shared.v4.u32 {{oa0, oa1, oa2, oa3}}, [{ENT}];")
+        if dual:
+            emit(f"    ld.shared.v4.u32 {{ob0, ob1, ob2, ob3}}, [{ENT}+16];")
+        emit(f"    ld.shared.u32 dl, [{ENT}+{o_dl}];")
+
+    def load_entry_fracs():
+        emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+{o_f}];")
+        emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+{o_g}];")
+
+    def entry_tail():
+        """addresses of the next window A, first direction's predicates"""
+        for c in range(4):
+            emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+        preds(0)
+
+    def subtree(r, lo, bit, tag):
+        """standard tree over targets [lo, lo + 2^(bit+1)) & <= kmax using bits bit..0, leaves jump to the bodies"""
         if bit < 0:
-            emit(f"    bra.uni B{r}_{d0};")
+            emit(f"    bra.uni B{r}_{lo};")
             return
-        hi = d0 + (1 << bit)
+        hi = lo + (1 << bit)
         if hi > kmax:
-            jump_tree(r, d0, bit - 1)
+            subtree(r, lo, bit - 1, tag)
             return
-        uid[0] += 1
-        lab = f"N{uid[0]}"
+        lab = f"T{tag}_{hi}_{bit}"
         emit(f"    @p{bit} bra.uni {lab};")
-        jump_tree(r, d0, bit - 1)
+        subtree(r, lo, bit - 1, tag)
         emit(f"{lab}:")
-        jump_tree(r, hi, bit - 1)
+        subtree(r, hi, bit - 1, tag)
+
+    need = set()   # shared subtrees S{r}_{base}_{b}: targets [base, base + 2^b)
+
+    def tree_from(r, dd):
+        """dispatch of direction r, falling through into B{r}_{dd}"""
+        for b in reversed(range(nbits)):
+            want = (dd >> b) & 1
+            base = ((dd >> (b + 1)) << (b + 1)) | ((1 - want) << b)
+            if base > kmax:
+                continue
+            need.add((r, base, b))
+            emit(f"    @{'!' if want else ''}p{b} bra.uni S{r}_{base}_{b};")
 
     emit("{")
-    emit(f"    .reg .pred p<{nbits}>, ploop;")
-    emit("    .reg .b32 x, dl, o<4>;")
+    emit(f"    .reg .pred p<{nbits}>, ploop, q;")
+    emit("    .reg .b32 x, dl, oa<4>, ob<4>;")
     emit("    .reg .f32 f<4>, g<4>;")
     emit(f"    .reg .b64 ff<4>, gg<4>, w<{nw}>;")
-    emit(f"    ld.shared.v4.u32 {{o0, o1, o2, o3}}, [{ENT}];")
-    emit(f"    ld.shared.u32 dl, [{ENT}+16];")
-    emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+32];")
-    emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+48];")
+    load_entry_head()
+    load_entry_fracs()
+    entry_tail()
+    if os.environ.get("BFLK_GEN_EXP") == "nolds":
+        window("oa")
+        first_window[0] = False
     emit("TOP:")
-    for c in range(4):
-        emit(f"    add.u32 o{c}, o{c}, {ROWR};")
-    for m in range(nch):
-        emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [o{m & 3}+{16 * (m + (m >> 2))}];")
-    emit(f"    add.u32 {ENT}, {ENT}, 64;")
-    emit(f"    add.u32 {ROWR}, {ROWR}, {RB};")
-    emit(f"    add.u32 {CNT}, {CNT}, -1;")
-    emit(f"    setp.ne.u32 ploop, {CNT}, 0;")
-    preds(0)
+    window("oa")
     for r in range(4):
         emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
         emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
-    jump_tree(0, 0, nbits - 1)
-    for r in range(4):
-        for dd in range(kmax + 1):
+    tree_from(0, 0)
+    for dd in range(kmax + 1):
+        for r in range(4):
             emit(f"B{r}_{dd}:")
-            if r < 3:
-                preds(r + 1)
+            if r == 0:
+                preds(1)
                 body(r, dd)
-                jump_tree(r + 1, 0, nbits - 1)
+                tree_from(1, dd)
+            elif r == 1:
+                preds(2)
+                if dual:
+                    emit(f"    and.b32 x, dl, {1 << 28};")
+                    emit("    setp.ne.b32 q, x, 0;")
+                    for c in range(4):
+                        emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
+                body(r, dd)
+                if dual:
+                    emit(f"    @q bra.uni SW_{dd};")
+                    window("ob")
+                    emit(f"SW_{dd}:")
+                tree_from(2, dd)
+            elif r == 2:
+                preds(3)
+                body(r, dd)
+                tree_from(3, dd)
             else:
-                # the next channel's entry: offsets + deltas now (dead since the window loads / predicates), fractions
-                # after the last FFMA2 that reads them (the read past a stage's last entry is never used)
-                emit(f"    ld.shared.v4.u32 {{o0, o1, o2, o3}}, [{ENT}];")
-                emit(f"    ld.shared.u32 dl, [{ENT}+16];")
+                emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+                load_entry_head()
+                emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
                 body(r, dd)
-                emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+32];")
-                emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+48];")
+                load_entry_fracs()
+                entry_tail()
                 emit("    @ploop bra.uni TOP;")
                 emit("    bra.uni DONE;")
+    for (r, base, b) in sorted(need):
+        emit(f"S{r}_{base}_{b}:")
+        subtree(r, base, b - 1, f"{r}_{base}_{b}")
     emit("DONE:")
     emit("}")
     asm = "\n".join(f'        "{ln}\\n"' for ln in L)
-    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K)] + ['"+r"(ent)', '"+r"(row)', '"+r"(cnt)'])
-    return f"""// NCH = {nch}: window of {nw} sample pairs, deltas 0..{kmax}
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(K)] + ['"+r"(ent)'])
+    name = "tile_stage_fast_dual" if dual else "tile_stage_fast"
+    return f"""// NCH = {nch}: {'two windows' if dual else 'window'} of {nw} sample pairs, deltas 0..{kmax}
 template <>
-__device__ __forceinline__ void tile_stage_fast<{nch}>(u64 (&acc)[4][{K}], uint32_t ent, uint32_t row, uint32_t cnt, uint32_t rb) {{
+__device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[4][{K}], uint32_t ent, uint32_t row, uint32_t end) {{
     asm volatile(
 {asm}
         : {outs}
-        : "r"(rb)
+        : "r"(row), "r"(end)
         : "memory");
 }}
 """
@@ -417,10 +478,14 @@ if "--fast" in sys.argv:
     print("// GENERATED by tools/gen_tile_asm.py --fast -- do not edit.  See that script for the why.")
     print("""// All channels of one pipeline stage for one tile, two-FMA form (tolerance mode).
 template <int NCH>
-__device__ __forceinline__ void tile_stage_fast(u64 (&acc)[4][8], uint32_t ent, uint32_t row, uint32_t cnt, uint32_t rb);
+__device__ __forceinline__ void tile_stage_fast(u64 (&acc)[4][8], uint32_t ent, uint32_t row, uint32_t end);
+template <int NCH>
+__device__ __forceinline__ void tile_stage_fast_dual(u64 (&acc)[4][8], uint32_t ent, uint32_t row, uint32_t end);
 """)
     for nch in (5, 6, 7, 8, 9, 10):
         print(gen_fast(nch))
+    for nch in (6, 7):
+        print(gen_fast(nch, dual=True))
     sys.exit(0)
 
 print("// GENERATED by tools/gen_tile_asm.py -- do not edit.  See that script for the why.")
