@@ -410,7 +410,7 @@ static int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
 }
 
 // Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.
-static int ensure_tiles(bflk_handle *h, bool fast) {
+static int ensure_tiles(bflk_handle *h, int fast) {
     if (h->tiles_valid && h->tiles_fast == fast) return BFLK_OK;
     h->tiles_valid = true;
     h->tiles_fast = fast;
@@ -450,10 +450,12 @@ static int ensure_tiles(bflk_handle *h, bool fast) {
         if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
     }
     if (fast) {
-        // the two-FMA variant keeps no differences, so one window of up to 10 chunks fits its registers; two 6- / 7-chunk
-        // windows (small dispatch trees, small code) are still faster once the 2x2 spread needs more than 7 chunks
+        // the two-FMA variant keeps no differences, so one window of up to 10 chunks fits its registers; two 6-chunk
+        // windows (2-bit dispatch trees, small code, the second one skipped where the tile fits the first) are still
+        // faster as soon as the 2x2 spread needs more than 6 chunks (measured: cfg2 0.576 vs 0.568, cfg3 0.539 vs 0.455)
         mode = 0;
-        if (span0 > 5 && pair_span <= 5) mode = pair_mode;
+        if (span0 > 3 && pair_span <= 3) mode = pair_mode;
+        else if (span0 > 7 && pair_span <= 5) mode = pair_mode;
         if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
             const int v = atoi(env);
             if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
@@ -461,7 +463,7 @@ static int ensure_tiles(bflk_handle *h, bool fast) {
     }
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[mode];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast ? 1 : 0);
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast);
     h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
     if (!h->tiles_usable) return BFLK_OK;
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
@@ -471,7 +473,7 @@ static int ensure_tiles(bflk_handle *h, bool fast) {
     BFLK_CUDA(h, cudaMemsetAsync(h->d_tiles.p, 0, entries * ent_bytes, h->stream));
     BFLK_CUDA(h, launch_build_tiles(h->d_off.p, h->d_frac.p, h->cfg.n_channels, h->d_index.p, usable, h->rows, cols,
                                     h->dir_first, h->dir_count, stage_off, h->tile_geom.copy_bytes, h->tile_geom.warps, mode,
-                                    2 * h->tile_geom.nch - 9, fast ? 1 : 0, h->d_tiles.p,
+                                    2 * h->tile_geom.nch - 9, fast, h->d_tiles.p,
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -548,7 +550,7 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
     bool tiled = false;
     if (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4) {
         // automatic choice = the two-FMA variant (power within the 1e-4 bar); 2 asks for bit-identical delayed sums
-        int rc = ensure_tiles(h, h->kernel_choice != 2);
+        int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0);
         if (rc) return rc;
         tiled = h->tiles_usable && !(row_stride & 1) && !((uintptr_t)stream_dev & 7);  // packed rows: 8-byte loads
         if (h->kernel_choice != 0 && !tiled)

@@ -68,7 +68,7 @@ struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
     int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
     int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
-    int fast = 0;        // 1: two-FMA form (TileEntryFast tables, one window per tile)
+    int fast = 0;        // 1: two-FMA form (TileEntryFast / TileEntryFastDual tables)
     int mode = 0;        // 0: one window per tile; 1 / 2: one window per direction pair (rows of a column / columns of a row)
     int row_chunks = 0;  // logical chunks per packed row
     int copy_bytes = 0;  // padded bytes of one copy of a packed row
@@ -159,7 +159,7 @@ struct bflk_handle {
     // register-tiled kernel tables (built lazily for the current grid / mask / range)
     bool tiles_valid = false;
     bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
-    bool tiles_fast = false;     // the tables were built for the two-FMA variant
+    int tiles_fast = 0;          // the tables were built for the two-FMA variant
     int32_t n_tiles = 0;
     int32_t tile_smax = 0;       // compiled window slack the tables need
     bflk::DevBuf<char> d_tiles;             // tile_table_entries(n_tiles, usable) TileEntry / TileEntryFast, layout above

@@ -30,7 +30,9 @@ namespace bflk {
 namespace {
 
 constexpr int kCC = kTileCC;         // channels per pipeline stage
-constexpr int kStages = 3;
+constexpr int kMaxStages = 4;        // stage buffers (KernelArgs::stages: 4 when shared memory allows, else 3)
+constexpr int kAhead = 2;            // stages in flight ahead of the consumers; with 4 buffers the producer thread refills
+                                     // the buffer every warp left TWO stages ago, so it never waits for a slow warp
 constexpr int kBlock = 256;          // output samples per block
 constexpr int kK = 8;                // sample pairs per lane
 constexpr int kFastMaxNch16 = 10;    // largest window of the two-FMA variant that still runs 16 warps per CTA
@@ -107,6 +109,7 @@ struct KernelArgs {
     int n_items, blocks_per_frame, frame_len;
     int pair0, n_pairs;          // block pairs [pair0, pair0 + n_pairs) of this launch ...
     int pairs_per_cta;           // ... consecutive ones handled by one CTA (short channel lists: amortises the ramp-up)
+    int stages;                  // stage buffers in shared memory (3 or 4)
     float *out;                  // power [frames][n_dir] (blocks_per_frame == 1) or partial [items][n_dir]
     float norm;
 };
@@ -116,15 +119,16 @@ struct KernelArgs {
 
 // DUAL: two NCH-chunk windows per channel, one per direction pair (tile tables built with mode 1 / 2), NCH 6 or 7
 // FAST: two-FMA form acc += g s[i+1]; acc += f s[i] (TileEntryFast tables; power within 1e-4 of the reference instead of
-//       bit-identical delayed sums) -- 16 FFMA2 per (direction, channel) and no other FP instruction
+//       bit-identical delayed sums) -- 16 FFMA2 per (direction, channel) and no other FP instruction.
 template <int NCH, int kWarps, bool DUAL = false, bool FAST = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kEnt = FAST ? (DUAL ? (int)sizeof(TileEntryFastDual) : (int)sizeof(TileEntryFast)) : (int)sizeof(TileEntry);
-    // layout: [kStages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * kEnt } then barriers
+    // layout: [stages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * kEnt } then barriers
     const int stage_rows = kCC * a.row_bytes;
     const int stage_bytes = stage_rows + kWarps * kCC * kEnt;
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int kStages = a.stages;
     const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages], empty[kStages]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,9 +151,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     __syncthreads();
 
     const int total_stages = n_stage * (pair_hi - pair_lo);
-    auto issue = [&](int g) {  // producer: one thread fills buffer g % kStages with global stage g = (pair, channel chunk)
+    auto issue = [&](int g, int buf) {  // producer: one thread fills buffer buf = g % stages with global stage g = (pair, channel chunk)
         const int pair = pair_lo + g / n_stage, st = g % n_stage;
-        const int buf = g % kStages;
         const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
         const uint32_t dst = smem + buf * stage_bytes;
         const uint32_t full = bars + 8 * buf;
@@ -159,10 +162,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC) * kEnt, tile_bytes, full);
     };
     if (threadIdx.x == 0)
-        for (int g = 0; g < min(kStages - 1, total_stages); g++) issue(g);
+        for (int g = 0; g < min(kAhead, total_stages); g++) issue(g, g);
 
     const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
     int gs = 0;                            // stages consumed so far by this CTA
+    int buf = 0, ph = 0;                   // buffer and barrier parity of stage gs
+    int pbuf = kAhead, pround = 0;         // buffer of stage gs + kAhead, parity of its round through the buffers
     for (int pair = pair_lo; pair < pair_hi; pair++) {
     u64 acc[4][kK];
 #pragma unroll
@@ -171,13 +176,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         for (int k = 0; k < kK; k++) acc[r][k] = 0ull;
 
     for (int st = 0; st < n_stage; st++, gs++) {
-        const int buf = gs % kStages;
-        // refill the buffer every warp left one stage ago with the chunk two stages ahead
-        if (threadIdx.x == 0 && gs + kStages - 1 < total_stages) {
-            if (gs >= 1) mbar_wait(bars + 8 * (kStages + (gs - 1) % kStages), ((gs - 1) / kStages) & 1);
-            issue(gs + kStages - 1);
+        // refill the buffer every warp left stages - kAhead stages ago with the chunk kAhead stages ahead
+        if (threadIdx.x == 0 && gs + kAhead < total_stages) {
+            if (gs + kAhead >= kStages) mbar_wait(bars + 8 * (kStages + pbuf), pround ^ 1);
+            issue(gs + kAhead, pbuf);
         }
-        mbar_wait(bars + 8 * buf, (gs / kStages) & 1);
+        mbar_wait(bars + 8 * buf, ph);
         const uint32_t rows_s = smem + buf * stage_bytes;
         const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * kEnt;
         const int nc = min(kCC, a.usable - st * kCC);
@@ -207,6 +211,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 8 * (kStages + buf));
+        if (++buf == kStages) { buf = 0; ph ^= 1; }
+        if (++pbuf == kStages) { pbuf = 0; pround ^= 1; }
     }
 
     // ---- epilogue: MA = 0.5 out[j] - 0.25 (out[j+1] + out[j-1]); power = sum MA^2 (mimo.cpp:131-137) ----
@@ -350,7 +356,11 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     const int kWarps = a.geom.warps;
     const size_t ent_bytes = das_tile_entry_bytes(a.geom);
     // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
-    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * kStages * 8 + 96;
+    int stages = kMaxStages;
+    auto smem_for = [&](int n) { return (size_t)n * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * n * 8 + 96; };
+    if (const char *env = getenv("BFLK_TILE_STAGES")) stages = atoi(env) == 3 ? 3 : 4;  // tuning knob
+    if (smem_for(stages) > 227 * 1024) stages = 3;
+    const size_t smem = smem_for(stages);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 
     KernelArgs k{};
@@ -366,6 +376,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     k.frame_len = a.frame_len;
     k.out = nblk == 1 ? a.power : a.partial;
     k.norm = a.norm;
+    k.stages = stages;
 
     // grid.y / grid.z are limited to 65535: process the pairs in slabs
     const int max_slab = 32768;

@@ -473,6 +473,12 @@ __device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[4][{K}], uint32_t ent, 
 """
 
 
+# Measured and rejected: a double-buffered flavour (window B of a channel in flight to a second register set while slots
+# 0,1 run on window A, then window A of the next channel while slots 2,3 run): ~165 registers -> 12 warps per CTA (the
+# register file is split per scheduler, so 14 warps still cap a thread at 128), always two window loads per channel ->
+# shared memory 79 % busy and 0.45 of the FP32 peak on every configuration (profiles/README.md).
+
+
 import sys
 if "--fast" in sys.argv:
     print("// GENERATED by tools/gen_tile_asm.py --fast -- do not edit.  See that script for the why.")
