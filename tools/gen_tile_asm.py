@@ -432,11 +432,13 @@ def gen_fast(nch, dual=False):
                 if dual:
                     emit(f"    and.b32 x, dl, {1 << 28};")
                     emit("    setp.ne.b32 q, x, 0;")
-                    for c in range(4):
-                        emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
                 body(r, dd)
                 if dual:
+                    # address adds inside the skipped block: ten instructions are too many for ptxas to if-convert, so a
+                    # tile that fits window A really branches around them instead of issuing six predicated-off loads
                     emit(f"    @q bra.uni SW_{dd};")
+                    for c in range(4):
+                        emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
                     window("ob")
                     emit(f"SW_{dd}:")
                 tree_from(2, dd)
