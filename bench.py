@@ -51,10 +51,16 @@ def parse():
 
 
 def default_frames(c):
-    # input stream = C x (B + 3) x N floats; 268 MB at cfg3 with B = 512 (L2 is 126 MB)
+    # input stream = C x (B + 3) x N floats, at least 256 MB (L2 is 126 MB).  The kernel works on pairs of 256-sample
+    # blocks, one CTA per (16 direction tiles, block pair): B is rounded up so that the number of block pairs is a
+    # multiple of the 148 SMs -- the CTAs then fill whole waves at 1, 2, 4 and 8 GPUs (cfg3: B = 592, 310 MB)
     C = 64 * c["nx"] * c["ny"]
     per_frame = C * c["N"] * 4
-    return max(2, int(np.ceil(256e6 / per_frame)))
+    B = max(2, int(np.ceil(256e6 / per_frame)))
+    if c["N"] == 256:
+        pairs = -(-B // 2)
+        B = 2 * (-(-pairs // 148) * 148)
+    return B
 
 
 def workload(c, name, B):
@@ -64,7 +70,8 @@ def workload(c, name, B):
     T += T & 1
     return dict(workload=f"{name}: {C} mics x {c['rows']}x{c['cols']}={D} directions x {c['N']}-sample frames",
                 channels=C, directions=D, frame_len=c["N"], frames_per_step=B, samples_per_channel=T,
-                input_mb=round(C * T * 4 / 1e6, 1), l2="inputs larger than L2 (126 MB); no flush needed")
+                input_mb=round(C * T * 4 / 1e6, 1), l2="inputs larger than L2 (126 MB); no flush needed",
+                frames_rule="256 MB of input, block pairs rounded up to a multiple of 148 SMs (whole CTA waves at 1-8 GPUs)")
 
 
 def flops_per_map(C, D, N):
