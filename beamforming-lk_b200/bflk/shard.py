@@ -42,3 +42,30 @@ def assemble(gathered, n_directions):
     if all(c == padded for c in counts):
         return gathered.permute(1, 0, 2).reshape(B, world * padded)
     return torch.cat([gathered[r, :, :counts[r]] for r in range(world)], dim=1)
+
+
+def channel_slice(n_channels, world, rank):
+    """(first, count) of the channel rows rank uploads in replicate_input (equal slices; the last rank takes the rest)."""
+    per = -(-n_channels // world)
+    first = min(rank * per, n_channels)
+    return first, min(per, n_channels - first)
+
+
+def replicate_input(host_stream, dev_stream, group=None, staging=None):
+    """Every rank needs ALL channels of the batch (the grid is sharded by direction, not by channel).  Instead of
+    each rank pulling the whole [C][T] stream over its own PCIe link, rank g uploads only its C / G channel rows
+    (G links in parallel) and one all-gather over NVLink replicates them: the channel-major layout makes the
+    concatenation of the slices the stream itself.  host_stream: pinned [C][T] tensor, dev_stream: [C][T] on the
+    device.  Falls back to a plain full copy when C is not a multiple of the world size."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    C, T = host_stream.shape
+    if world == 1 or C % world:
+        dev_stream.copy_(host_stream, non_blocking=True)
+        return dev_stream
+    first, count = channel_slice(C, world, rank)
+    if staging is None:
+        staging = torch.empty((count, T), dtype=dev_stream.dtype, device=dev_stream.device)
+    staging.copy_(host_stream[first:first + count], non_blocking=True)
+    dist.all_gather_into_tensor(dev_stream.view(world * count, T), staging, group=group)
+    return dev_stream

@@ -230,6 +230,7 @@ def run_ours(args, c, name):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.frames or default_frames(c)
@@ -311,8 +312,11 @@ def run_ours(args, c, name):
         else:
             full = gathered
 
+            slice_dev = torch.empty((C // world, T), dtype=torch.float32, device=dev) if C % world == 0 else None
+
             def e2e_step():
-                stream_dev.copy_(host_in, non_blocking=True)
+                # each rank uploads C / G channel rows over its own PCIe link, one NVLink all-gather replicates them
+                shard.replicate_input(host_in, stream_dev, staging=slice_dev)
                 step()
                 host_out.copy_(shard.assemble(full, D), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -329,7 +333,10 @@ def run_ours(args, c, name):
             ems = timed(e2e_step, e2e_steps, 1)
         e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": C * T * 4,
                "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
-               "path": "bflk_power_map_batch (host buffers)" if world == 1 else "pinned H2D + bflk_power_map_batch_dev + all_gather + D2H"}
+               "path": "bflk_power_map_batch (host buffers)" if world == 1 else
+               "pinned H2D of C/G channel rows per rank + input all_gather + bflk_power_map_batch_dev + map all_gather + D2H"}
+        if world > 1:
+            e2e["h2d_bytes_per_step"] = C * T * 4        # summed over the ranks (each uploads 1 / G of it)
 
     if rank == 0:
         pk, pk_kind = peaks()

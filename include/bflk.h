@@ -105,11 +105,14 @@ int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out);
 /* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream);
-/* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel,
- * 3 = lane-broadcast kernel. */
+/* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel with the reference's
+ * exact operation triple (delayed sums bit-identical to delay(), src/dsp/delay.cpp:16-26), 3 = lane-broadcast kernel,
+ * 4 = register-tiled kernel in two-FMA form (f*s[i] + (1-f)*s[i+1]: as accurate as the reference against exact
+ * arithmetic, power maps within the 1e-4 bar, ~13 % faster than 2).  Automatic = 4 when the grid tiles, else 3, else 1. */
 int bflk_set_kernel(bflk_handle *h, int32_t which);
-/* Which kernel the last power-map call used (1 generic, 2 tiled, 3 lane-broadcast; 0 = none yet), the largest offset spread
- * inside a 2x2 direction tile for the current grid, and the window chunks of the tiled variant in use. */
+/* Which kernel the last power-map call used (1 generic, 2 tiled exact, 3 lane-broadcast, 4 tiled two-FMA; 0 = none yet), the
+ * largest offset spread inside a direction tile (or tile pair) for the current grid, and the window chunks of the tiled
+ * variant in use. */
 int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t bflk_launch_count(const bflk_handle *h);

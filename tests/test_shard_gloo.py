@@ -57,6 +57,33 @@ def test_sharded_maps_assemble_to_full_map(tmp_path, world, rows, cols):
     assert np.array_equal(full, ref)          # same oracle arithmetic per direction -> bit-identical after assembly
 
 
+def _input_worker(rank, world, port, C, T, out_path):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bflk import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    host = torch.arange(C * T, dtype=torch.float32).reshape(C, T) * 0.5
+    devt = torch.full((C, T), -1.0)
+    shard.replicate_input(host, devt)
+    ok = torch.equal(devt, host)
+    flags = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([float(ok)]))
+    if rank == 0:
+        np.save(out_path, np.array([f.item() for f in flags]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,C", [(2, 64), (4, 64), (3, 64)])      # 64 % 3 != 0: full-copy fallback
+def test_channel_sliced_upload_replicates_the_stream(tmp_path, world, C):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_input_worker, args=(world, _free_port(), C, 300, out), nprocs=world, join=True)
+    assert np.all(np.load(out) == 1.0)
+
+
 def test_direction_shard_partition():
     import sys
     if PKG not in sys.path:
