@@ -31,7 +31,7 @@ SYMBOLS = [
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
-    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev",
+    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev", "bflk_monopulse",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
 ]
 
@@ -91,6 +91,7 @@ def load_library():
     L.bflk_kernel_time_ms.argtypes = [vp, C.POINTER(f32), C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
     L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.bflk_miso_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+    L.bflk_monopulse.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
     L.bflk_calibrate.argtypes = [vp, vp, i32, f32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
     L.bflk_ingest_i32.argtypes = [vp, vp, i32, i32, vp]
@@ -276,6 +277,19 @@ class Beamformer:
         self._check(self._L.bflk_miso(self._h, _ptr(theta), _ptr(phi), T, _ptr(window),
                                       _ptr(audio) if want_audio else None, _ptr(power) if want_power else None))
         return audio, power
+
+    def monopulse(self, theta, phi, window, spread, theta_limit, reference=0.0):
+        """GradientParticle::findNearby + the beam part of step() for P particles: returns (theta' [P], near_theta [P][4],
+        near_phi [P][4], q [P][4], gradient [P][3] = (theta, phi, radius), error [P])."""
+        theta, phi = _np(theta, np.float64).ravel().copy(), _np(phi, np.float64).ravel()
+        window = _np(window, np.float32)
+        assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
+        P = theta.shape[0]
+        nth, nph, q = np.zeros((P, 4)), np.zeros((P, 4)), np.zeros((P, 4))
+        grad, err = np.zeros((P, 3)), np.zeros(P)
+        self._check(self._L.bflk_monopulse(self._h, _ptr(theta), _ptr(phi), P, C.c_double(spread), C.c_double(theta_limit),
+                                           C.c_double(reference), _ptr(window), _ptr(nth), _ptr(nph), _ptr(q), _ptr(grad), _ptr(err)))
+        return theta, nth, nph, q, grad, err
 
     # -- neighbours ---------------------------------------------------------------------------------------------
     def heatmap(self, power):

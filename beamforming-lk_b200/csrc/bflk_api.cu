@@ -782,6 +782,71 @@ int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_
     return BFLK_OK;
 }
 
+// ---- monopulse step ---------------------------------------------------------------------------
+// Spherical::quadrant + normalizeSpherical in double on the host (geometry.cpp:181-217, :120-142, :11-20; particle.h:24-27).
+// Eigen's 3x3 / 4x3 products are pinned as ((a0 b0 + a1 b1) + a2 b2) without contraction (this file is built with
+// -ffp-contract=off), the same order oracle/oracle.c uses.
+static inline double dot3(const double *a, const double *b, int sb) { return (a[0] * b[0] + a[1] * b[sb]) + a[2] * b[2 * sb]; }
+
+static void quadrant_directions(double *theta, double phi, double spread, double theta_limit, double *near_theta, double *near_phi) {
+    static const double deg[4] = {45.0, 315.0, 225.0, 135.0};
+    double search[4][3];
+    for (int i = 0; i < 4; i++) {
+        const double a = deg[i] * (M_PI / 180.0);
+        search[i][0] = 1.0 * sin(spread) * cos(a);
+        search[i][1] = 1.0 * sin(spread) * sin(a);
+        search[i][2] = 1.0 * cos(spread);
+    }
+    double rt = *theta;
+    if (rt + spread > M_PI / 2.0) {
+        rt -= spread;
+        *theta -= spread / 2.0;
+    }
+    const double Rz[9] = {cos(phi), -sin(phi), 0.0, sin(phi), cos(phi), 0.0, 0.0, 0.0, 1.0};
+    const double Ry[9] = {cos(rt), 0.0, sin(rt), 0.0, 1.0, 0.0, -sin(rt), 0.0, cos(rt)};
+    double R[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R[3 * i + j] = dot3(Ry + 3 * i, Rz + j, 3);
+    for (int i = 0; i < 4; i++) {
+        double k[3];
+        for (int j = 0; j < 3; j++) k[j] = dot3(search[i], R + j, 3);
+        double nt = acos(k[2]);
+        double np = fmod(atan2(k[1], k[0]) - M_PI, 2.0 * M_PI);
+        if (np < 0.0) np = 2.0 * M_PI + np;
+        nt = nt < 0.0 ? 0.0 : (nt > theta_limit ? theta_limit : nt);
+        near_theta[i] = nt;
+        near_phi[i] = np;
+    }
+}
+
+int bflk_monopulse(bflk_handle *h, double *theta, const double *phi, int32_t n_particles, double spread,
+                   double theta_limit, double reference, const float *window, double *near_theta, double *near_phi,
+                   double *q, double *gradient, double *error) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!theta || !phi || n_particles <= 0 || !window) return h->fail(BFLK_ERR_INVALID, "bflk_monopulse: null / empty arguments");
+    const int T = 4 * n_particles;
+    std::vector<double> nth(T), nph(T);
+    for (int p = 0; p < n_particles; p++) quadrant_directions(&theta[p], phi[p], spread, theta_limit, &nth[4 * p], &nph[4 * p]);
+    std::vector<float> power(T);
+    int rc = bflk_miso(h, nth.data(), nph.data(), T, window, nullptr, power.data());   // one launch for all beams
+    if (rc) return rc;
+    for (int p = 0; p < n_particles; p++) {
+        const double q1 = power[4 * p], q2 = power[4 * p + 1], q3 = power[4 * p + 2], q4 = power[4 * p + 3];   // beam() returns double
+        const double sum = q1 + q2 + q3 + q4;
+        const double gphi = (q1 + q4) - (q2 + q3), gtheta = (q3 + q4) - (q1 + q2);
+        if (error) error[p] = (fabs(gphi) + fabs(gtheta)) / sum;
+        if (gradient) {
+            gradient[3 * p] = reference > 0.0 ? gtheta / reference : gtheta;
+            gradient[3 * p + 1] = reference > 0.0 ? gphi / reference : gphi;
+            gradient[3 * p + 2] = sum / 4;
+        }
+        if (q) { q[4 * p] = q1; q[4 * p + 1] = q2; q[4 * p + 2] = q3; q[4 * p + 3] = q4; }
+    }
+    if (near_theta) std::memcpy(near_theta, nth.data(), T * sizeof(double));
+    if (near_phi) std::memcpy(near_phi, nph.data(), T * sizeof(double));
+    return BFLK_OK;
+}
+
 // ---- neighbours of the path ------------------------------------------------------------------------------------
 int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv) {
     if (!h) return BFLK_ERR_INVALID;

@@ -131,6 +131,20 @@ int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_
 int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets,
                   const float *window_dev, float *audio_dev, float *power_dev, void *cuda_stream);
 
+/* Monopulse step of the gradient tracker (GradientParticle::findNearby + the beam part of GradientParticle::step,
+ * quadrant form, src/dsp/gradient_ascend.cpp:18-81).  For each particle p: the four quadrant directions at angular
+ * distance `spread` around (theta[p], phi[p]) (Spherical::quadrant, src/geometry/geometry.cpp:181-217 -- like the
+ * reference it pulls theta[p] in by spread / 2 when theta + spread would pass pi / 2 and writes that back),
+ * normalised to phi in [0, 2 pi), theta in [0, theta_limit] (normalizeSpherical, src/dsp/particle.h:24-27); their beam
+ * powers q[p][4] (Particle::steer + Particle::beam) in ONE batched launch for all 4 * n_particles beams;
+ * gradient[p][3] = {theta, phi, radius} = {((q3+q4)-(q1+q2)) / reference, ((q1+q4)-(q2+q3)) / reference, sum / 4}
+ * (reference <= 0: not divided, the RELATIVE 0 build) and error[p] = (|phi| + |theta|) / sum of the undivided values.
+ * The particle update itself (Particle::step, jump / tracking heuristics) stays with the caller.
+ * near_theta / near_phi / q are [n_particles][4]; any output may be NULL. */
+int bflk_monopulse(bflk_handle *h, double *theta, const double *phi, int32_t n_particles, double spread,
+                   double theta_limit, double reference, const float *window, double *near_theta, double *near_phi,
+                   double *q, double *gradient, double *error);
+
 /* ---- neighbours of the path ------------------------------------------------------------------------ */
 /* populateHeatmap: heat[count] = uchar(clip(255 * p / max)), argmax / max of the map. */
 int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv);

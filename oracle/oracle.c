@@ -237,3 +237,54 @@ void orc_ingest(const int32_t *frames, int n, int n_sensors, float *exposure) {
         }
     }
 }
+
+/* ---- f2: monopulse directions and gradient (next row of SURVEY 8f) ------------------------- */
+/* Spherical::quadrant (src/geometry/geometry.cpp:181-217) with rotateTo (:120-142), toCartesian (:91-98) and
+ * normalizeSpherical (src/dsp/particle.h:24-27; wrapAngle src/geometry/geometry.cpp:11-20).  All double.  The 3x3
+ * and 4x3 products go through Eigen in the reference (absent here): the order is fixed as ((a0 b0 + a1 b1) + a2 b2),
+ * no contraction.  *theta is pulled in by spread / 2 when theta + spread passes pi / 2, like the reference's
+ * non-const member does to directionCurrent. */
+static double dot3(const double *a, const double *b, int sb) { return (a[0] * b[0] + a[1] * b[sb]) + a[2] * b[2 * sb]; }
+
+void orc_quadrant(double *theta, double phi, double spread, double theta_limit, double *near_theta, double *near_phi) {
+    static const double deg[4] = {45.0, 315.0, 225.0, 135.0};
+    double search[4][3];
+    for (int i = 0; i < 4; i++) {
+        const double a = deg[i] * (M_PI / 180.0);                 /* TO_RADIANS, geometry.h:18 */
+        search[i][0] = 1.0 * sin(spread) * cos(a);                  /* radius * sin(theta) * cos(phi) */
+        search[i][1] = 1.0 * sin(spread) * sin(a);
+        search[i][2] = 1.0 * cos(spread);
+    }
+    double rt = *theta;
+    if (rt + spread > M_PI / 2.0) {                                /* geometry.cpp:198-201 */
+        rt -= spread;
+        *theta -= spread / 2.0;
+    }
+    const double Rz[9] = {cos(phi), -sin(phi), 0.0, sin(phi), cos(phi), 0.0, 0.0, 0.0, 1.0};
+    const double Ry[9] = {cos(rt), 0.0, sin(rt), 0.0, 1.0, 0.0, -sin(rt), 0.0, cos(rt)};
+    double R[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R[3 * i + j] = dot3(Ry + 3 * i, Rz + j, 3);   /* rotation = Ry * Rz */
+    for (int i = 0; i < 4; i++) {
+        double k[3];
+        for (int j = 0; j < 3; j++) k[j] = dot3(search[i], R + j, 3);              /* rotated = points * rotation */
+        double nt = acos(k[2]);
+        double np = atan2(k[1], k[0]) - M_PI;
+        np = fmod(np, 2.0 * M_PI);                                  /* wrapAngle */
+        if (np < 0.0) np = 2.0 * M_PI + np;
+        nt = nt < 0.0 ? 0.0 : (nt > theta_limit ? theta_limit : nt);   /* clip */
+        near_theta[i] = nt;
+        near_phi[i] = np;
+    }
+}
+
+/* GradientParticle::step, quadrant form (src/dsp/gradient_ascend.cpp:50-78): q[4] -> {theta, phi, radius}, error */
+void orc_monopulse_gradient(const double *q, double reference, double *gradient, double *error) {
+    const double sum = q[0] + q[1] + q[2] + q[3];
+    const double phi = (q[0] + q[3]) - (q[1] + q[2]);
+    const double theta = (q[2] + q[3]) - (q[0] + q[1]);
+    *error = (fabs(phi) + fabs(theta)) / sum;
+    gradient[0] = reference > 0.0 ? theta / reference : theta;     /* RELATIVE 1 / 0 */
+    gradient[1] = reference > 0.0 ? phi / reference : phi;
+    gradient[2] = sum / 4;
+}

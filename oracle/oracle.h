@@ -87,6 +87,10 @@ int orc_calibrate(const float *signals, int W, float reference_power_level, int 
  * frames[n][n_sensors] -> float exposure[n_sensors][n] with serpentine column un-flip and /2^23. */
 void orc_ingest(const int32_t *frames, int n, int n_sensors, float *exposure);
 
+/* f2: Spherical::quadrant + normalizeSpherical; GradientParticle::step (quadrant form) */
+void orc_quadrant(double *theta, double phi, double spread, double theta_limit, double *near_theta, double *near_phi);
+void orc_monopulse_gradient(const double *q, double reference, double *gradient, double *error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,10 @@ def lib():
         L.orc_mimo_das.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, C.c_int, _f32p]
         L.orc_particle_beam.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, _f32p]
         L.orc_particle_beam.restype = C.c_double
+        L.orc_quadrant.argtypes = [_f64p, C.c_double, C.c_double, C.c_double, _f64p, _f64p]
+        L.orc_quadrant.restype = None
+        L.orc_monopulse_gradient.argtypes = [_f64p, C.c_double, _f64p, _f64p]
+        L.orc_monopulse_gradient.restype = None
         L.orc_particle_das.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, _f32p]
         L.orc_populate_heatmap.argtypes = [_f32p, C.c_int, _u8p, C.POINTER(C.c_float)]
         L.orc_populate_heatmap.restype = C.c_int
@@ -223,3 +227,30 @@ def ref_mimo_update(window, offsets, fractions, index=None, n=N_SAMPLES, n_threa
                       np.ascontiguousarray(fractions, np.float32), D, power.ctypes.data,
                       das.ctypes.data if want_das else None, n_threads)
     return (power, das) if want_das else power
+
+
+def quadrant(theta, phi, spread, theta_limit):
+    """Spherical::quadrant + normalizeSpherical (geometry.cpp:181-217, particle.h:24-27): (theta', near_theta[4], near_phi[4])."""
+    t = np.array([theta], np.float64)
+    nt, nph = np.zeros(4), np.zeros(4)
+    lib().orc_quadrant(t, float(phi), float(spread), float(theta_limit), nt, nph)
+    return float(t[0]), nt, nph
+
+
+def monopulse(xyz, theta, phi, window, spread, theta_limit, reference=0.0, index=None):
+    """GradientParticle::findNearby + step() up to the gradient (gradient_ascend.cpp:18-81) for each particle, with the
+    oracle's steer / beam: (theta', near_theta, near_phi, q, gradient, error)."""
+    theta = np.asarray(theta, np.float64).ravel().copy()
+    phi = np.asarray(phi, np.float64).ravel()
+    P = theta.shape[0]
+    nth, nph, q = np.zeros((P, 4)), np.zeros((P, 4)), np.zeros((P, 4))
+    grad, err = np.zeros((P, 3)), np.zeros(P)
+    for p in range(P):
+        theta[p], nth[p], nph[p] = quadrant(theta[p], phi[p], spread, theta_limit)
+        off, fr = steer_tables(xyz, nth[p], nph[p])
+        for k in range(4):
+            q[p, k] = particle_beam(window, off[k], fr[k], index=index)
+        e = np.zeros(1)
+        lib().orc_monopulse_gradient(np.ascontiguousarray(q[p]), float(reference), grad[p], e)
+        err[p] = e[0]
+    return theta, nth, nph, q, grad, err

@@ -240,6 +240,32 @@ def test_cfg4_miso_vs_oracle(bf, oracle):
         assert abs(power[t] - oracle.particle_beam(window, off[t], fr[t])) <= POWER_RTOL * power[t]
 
 
+def test_monopulse_step_vs_oracle(bf, oracle):
+    """f2: quadrant directions bit-exact, the 4 x P beam powers within 1e-4, gradient and error from them."""
+    c = cases.CFG4
+    w = bf.MISOWorker(cases.origins(c["nx"], c["ny"]))
+    window = _synth_window(bf, c)
+    xyz = oracle.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    rng = np.random.default_rng(11)
+    P = 26                                                      # 16 seekers + 10 trackers (gradient_ascend.h)
+    limit = np.deg2rad(80.0)
+    theta = np.r_[rng.random(P - 3) * limit, limit - 1e-3, np.pi / 2 - 0.01, 0.0]      # incl. the pull-in branch and boresight
+    phi = rng.random(P) * 2 * np.pi
+    spread = np.deg2rad(4.0)
+    got = w.monopulse(theta, phi, window, spread, limit, reference=3e-4)
+    exp = oracle.monopulse(xyz, theta, phi, window, spread, limit, reference=3e-4)
+    assert np.array_equal(got[0], exp[0]) and not np.array_equal(got[0], theta)       # theta pulled in where it must
+    assert np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])          # directions: same doubles
+    assert rel_err(got[3], exp[3]) <= POWER_RTOL
+    scale = np.abs(exp[3]).sum(axis=1) / 3e-4                                         # gradient = differences of q / reference
+    assert np.all(np.abs(got[4][:, :2] - exp[4][:, :2]) <= 4 * POWER_RTOL * scale[:, None])
+    assert np.all(np.abs(got[4][:, 2] - exp[4][:, 2]) <= POWER_RTOL * exp[4][:, 2])
+    assert np.all(np.abs(got[5] - exp[5]) <= 8 * POWER_RTOL)
+    # the strongest source (20 deg, 30 deg) pulls a particle started next to it towards itself: positive radius, small error
+    t1, _, _, q, g, e = w.monopulse([np.deg2rad(21.0)], [np.deg2rad(31.0)], window, spread, limit)
+    assert g[0, 2] > 0 and np.all(q > 0)
+
+
 # ---- batching, sharding, masks, edge cases -----------------------------------------------------------------------
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_batch_equals_single_frames(bf, oracle, kernel):

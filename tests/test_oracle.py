@@ -170,3 +170,24 @@ def test_empty_and_ragged_masks(oracle, golden):
     rev = oracle.mimo_update(g["window"], off, fr, index=np.arange(63, -1, -1, dtype=np.int32))
     fwd = oracle.mimo_update(g["window"], off, fr)
     assert np.allclose(rev, fwd, rtol=1e-3)     # same physics, different rounding order
+
+
+def test_quadrant_directions_geometry(oracle):
+    """Spherical::quadrant (geometry.cpp:181-217): four directions at angular distance `spread` from the particle, 90
+    degrees apart around it; theta pulled in by spread / 2 only when theta + spread passes pi / 2; phi wrapped."""
+    def unit(t, p):
+        return np.array([np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)])
+    spread = np.deg2rad(5.0)
+    for theta, phi in [(0.3, 1.0), (1.2, 4.0), (0.0, 0.0), (np.pi / 2 - 0.02, 2.0)]:
+        t2, nt, nph = oracle.quadrant(theta, phi, spread, np.pi / 2)
+        pulled = theta + spread > np.pi / 2
+        assert t2 == (theta - spread / 2 if pulled else theta)
+        assert np.all((nph >= 0) & (nph < 2 * np.pi)) and np.all((nt >= 0) & (nt <= np.pi / 2))
+        v = np.stack([unit(a, b) for a, b in zip(nt, nph)])
+        # points * (Ry Rz) rotates the pole to a direction at polar angle (theta - spread if pulled) -- all four neighbours
+        # sit `spread` away from it, and opposite ones (0,2) / (1,3) are 2 * spread apart
+        centre = v.sum(axis=0) / np.linalg.norm(v.sum(axis=0))
+        assert np.allclose(np.arccos(np.clip(v @ centre, -1, 1)), spread, atol=1e-9)
+        assert np.isclose(np.arccos(np.clip(v[0] @ v[2], -1, 1)), 2 * spread, atol=1e-9)
+        assert np.isclose(np.arccos(np.clip(v[1] @ v[3], -1, 1)), 2 * spread, atol=1e-9)
+        assert np.isclose(np.arccos(centre[2]), theta - spread if pulled else theta, atol=1e-9)
