@@ -663,13 +663,27 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
     BFLK_CUDA(h, h->d_window.reserve(n_in));
     BFLK_CUDA(h, h->d_power.reserve(n_out));
     // Chunks of frames: the H2D copy of chunk k+1 (copy_stream) overlaps the kernels of chunk k (stream).
-    // A chunk is ~32 MiB of new samples so PCIe and the SMs both stay busy; small batches are one chunk.
+    // A chunk is ~32 MiB of new samples, rounded to whole CTA waves, so PCIe and the SMs both stay busy; small batches
+    // are one chunk.
     const int64_t tail = min_stream_samples(h, 1) - N;  // samples a frame needs beyond its own N
-    int64_t chunk_bytes = 64ll << 20;  // measured on B200 / PCIe 5: 64 MiB chunks beat 32 (2-D copy rows get too short) and 96
+    int64_t chunk_bytes = 32ll << 20;  // measured on B200 / PCIe 5 at cfg3 with wave-aligned chunks: 32 MiB 64.7 k maps/s, 64 MiB 61.6 k, 96 MiB 56.9 k
     if (const char *env = getenv("BFLK_CHUNK_MIB")) chunk_bytes = std::max(1, atoi(env)) * (1ll << 20);  // tuning knob
     const int64_t frame_bytes = (int64_t)C * N * sizeof(float);
     int n_chunks = (int)std::max<int64_t>(1, ((int64_t)n_frames * frame_bytes + chunk_bytes / 2) / chunk_bytes);
-    const int chunk_frames = (n_frames + n_chunks - 1) / n_chunks;  // even split
+    int chunk_frames = (n_frames + n_chunks - 1) / n_chunks;  // even split
+    if (n_chunks > 1 && N == 256 && h->kernel_choice != 1 && h->kernel_choice != 3 && h->sm_count > 0) {
+        // the tiled kernel runs one CTA per (tile group, block pair): round the chunk to a whole number of CTA waves
+        int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0);
+        if (rc) return rc;
+        if (h->tiles_usable) {
+            const int ctas_per_pair = (h->n_tiles + h->tile_geom.warps - 1) / h->tile_geom.warps;
+            int g = h->sm_count, b = ctas_per_pair;
+            while (b) { const int t = g % b; g = b; b = t; }          // gcd
+            const int quantum = 2 * (h->sm_count / g);                // frames per whole wave set
+            const int k = std::max(1, (chunk_frames + quantum / 2) / quantum);
+            if (k * quantum < n_frames) chunk_frames = k * quantum;
+        }
+    }
     n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
     if (!h->copy_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     while ((int)h->chunk_events.size() < n_chunks) {
