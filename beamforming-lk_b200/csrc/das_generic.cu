@@ -14,23 +14,36 @@ namespace bflk {
 constexpr int kGenericThreads = 256;
 
 __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArgs a) {
-    extern __shared__ float s_out[];  // [N + 2] delayed sum of this direction
+    // [N + 2] delayed sum of this direction | [usable] fraction | [usable] element offset of the channel's first tap.
+    // The per-channel table (mask index -> offset, fraction) is resolved once into shared memory: the channel loop
+    // then has no dependent global loads (index -> offset -> sample) and its sample loads pipeline across channels.
+    extern __shared__ __align__(8) unsigned char s_raw[];
     __shared__ float s_red[kGenericThreads / 32];
     const int d = blockIdx.x;
     const int b = blockIdx.y;
     const int N = a.frame_len;
+    long long *s_addr = reinterpret_cast<long long *>(s_raw);
+    float *s_frac = reinterpret_cast<float *>(s_raw + sizeof(long long) * a.usable);
+    float *s_out = s_frac + a.usable;
     const int32_t *off = a.off + (size_t)d * a.C;
     const float *frac = a.frac + (size_t)d * a.C;
     const float *base = a.stream + (size_t)b * a.frame_stride;
+    for (int s = threadIdx.x; s < a.usable; s += kGenericThreads) {
+        const int c = a.index[s];
+        s_addr[s] = (long long)c * a.row_stride + off[c];
+        s_frac[s] = frac[c];
+    }
+    __syncthreads();
 
     for (int i0 = 0; i0 < N; i0 += kGenericThreads) {
         const int i = i0 + threadIdx.x;
         float acc = 0.0f;
         if (i < N) {
+            const float *sig0 = base + i;
+#pragma unroll 8
             for (int s = 0; s < a.usable; s++) {
-                const int c = a.index[s];
-                const float *sig = base + (size_t)c * a.row_stride + off[c] + i;
-                const float f = frac[c];
+                const float *sig = sig0 + s_addr[s];
+                const float f = s_frac[s];
                 const float cur = __ldg(sig), nxt = __ldg(sig + 1);
                 acc = __fadd_rn(acc, __fmaf_rn(f, __fsub_rn(cur, nxt), nxt));
             }
@@ -58,7 +71,7 @@ __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArg
 
 cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st) {
     if (a.n_dir <= 0 || a.n_frames <= 0) return cudaSuccess;
-    size_t smem = (size_t)(a.frame_len + 2) * sizeof(float);
+    size_t smem = (size_t)(a.frame_len + 2) * sizeof(float) + (size_t)a.usable * (sizeof(long long) + sizeof(float));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(das_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -37,3 +37,8 @@ th, ph = cases.cfg4_targets()
 m.steer(th, ph)
 win = synth.make_stream(synth.tile_geometry(cases.origins(c["nx"], c["ny"])), 1024)
 print("cfg4: bflk_miso, 16 targets x 512 mics, audio[16][256] + beam power: " + timeit(lambda: m.update(win)))
+P = 26                                                           # 16 seekers + 10 trackers (gradient_ascend.h)
+rng = np.random.default_rng(5)
+pth, pph = rng.random(P) * np.deg2rad(70.0), rng.random(P) * 2 * np.pi
+print("f2: bflk_monopulse, 26 particles x 4 beams x 512 mics (quadrant directions, tables, beams, gradient): "
+      + timeit(lambda: m.monopulse(pth, pph, win, np.deg2rad(4.0), np.deg2rad(80.0), 3e-4)))
