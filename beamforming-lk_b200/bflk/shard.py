@@ -69,3 +69,37 @@ def replicate_input(host_stream, dev_stream, group=None, staging=None):
     staging.copy_(host_stream[first:first + count], non_blocking=True)
     dist.all_gather_into_tensor(dev_stream.view(world * count, T), staging, group=group)
     return dev_stream
+
+
+# ---- batches: direction groups x frame groups ----------------------------------------------------------------------
+# A batch of B frames has a second independent axis.  Sharding ONLY the grid makes every rank repeat the per-batch
+# pre-pass (the pack of the whole input: 3 % of a step on one GPU, 20 % on eight); sharding only the frames would leave
+# the grid whole.  The bench therefore arranges G ranks as G_d direction groups x G_f frame groups: rank r works on
+# direction slice r % G_d of frame slice r // G_d, the pre-pass is repeated G_d times instead of G times, and one
+# all-gather over all ranks assembles [B][D].  G_d = G is the pure grid sharding above.
+def grid_2d(world, dir_groups=0):
+    """(G_d, G_f): dir_groups if given (must divide world), else 2 direction groups when world is even."""
+    gd = dir_groups if dir_groups else (2 if world % 2 == 0 else 1)
+    if gd < 1 or world % gd:
+        raise ValueError(f"{gd} direction groups do not divide {world} ranks")
+    return gd, world // gd
+
+
+def frame_shard(n_frames, groups, g):
+    """(first, count) of frame group g: contiguous, even counts (the kernel works on block pairs), the last takes the rest."""
+    per = -(-n_frames // groups)
+    per += per & 1
+    first = min(g * per, n_frames)
+    return first, max(0, min(per, n_frames - first))
+
+
+def assemble_2d(gathered, n_frames, n_directions, gd, gf):
+    """[world][frames per group][padded directions] (rank r = frame group r // gd, direction group r % gd) -> [B][D]."""
+    world, nf, padded = gathered.shape
+    assert world == gd * gf
+    counts = shard_counts(n_directions, gd)
+    fcounts = [frame_shard(n_frames, gf, g)[1] for g in range(gf)]
+    if all(c == padded for c in counts) and all(c == nf for c in fcounts):
+        return gathered.view(gf, gd, nf, padded).permute(0, 2, 1, 3).reshape(gf * nf, gd * padded)
+    rows = [torch.cat([gathered[g * gd + d, :fcounts[g], :counts[d]] for d in range(gd)], dim=1) for g in range(gf)]
+    return torch.cat(rows, dim=0)

@@ -6,8 +6,10 @@
 A "step" is one pass of the hot path over one batch of B synthetic frames (C channels x (B+3)*N samples,
 larger than L2) for every direction of the grid.  N = 1 runs the configuration the target is quoted on
 (cfg3: 512 microphones x 32x32 = 1024 directions x 256-sample frames).  N > 1 (torchrun, one rank per GPU)
-shards the steering grid across ranks -- total work fixed, "strong" scaling -- and assembles the
-per-rank power-map slices with an NCCL all-gather inside the timed region.
+arranges the ranks as G_d direction groups x G_f frame groups (default G_d = 2; --dir-groups N = the grid sharded
+N ways): rank r computes direction slice r % G_d of the steering grid for frame slice r // G_d of the batch --
+total work fixed, "strong" scaling -- and one NCCL all-gather inside the timed region assembles the [B][D] maps
+on every rank.
 
 One JSON line on rank 0.  `value`: maps/s with inputs resident in HBM.  `e2e`: the same through the
 host-buffer C-ABI call (H2D of the batch + D2H of the maps inside the timed region).  `roofline`: the
@@ -45,6 +47,8 @@ def parse():
     ap.add_argument("--config", default="cfg3", choices=list(cases.CONFIGS))
     ap.add_argument("--frames", type=int, default=0, help="frames per step (default: sized so the input exceeds L2)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 register-tiled (bit-identical sums), 3 lane-broadcast, 4 register-tiled two-FMA form")
+    ap.add_argument("--dir-groups", type=int, default=0,
+                    help="N > 1: direction groups G_d (ranks = G_d x frame groups); 0 = 2 when N is even; N = pure grid sharding")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -237,21 +241,35 @@ def run_ours(args, c, name):
     C, D, N = 64 * c["nx"] * c["ny"], c["rows"] * c["cols"], c["N"]
     cfg = workload(c, name, B)
     T = cfg["samples_per_channel"]
-    first, count = shard.direction_shard(D, world, rank)
-    per = shard.padded_count(D, world)
+    # ranks = G_d direction groups x G_f frame groups (bflk/shard.py): rank r -> direction slice r % G_d of frame slice r // G_d
+    gd, gf = shard.grid_2d(world, args.dir_groups) if world > 1 else (1, 1)
+    dgrp, fgrp = rank % gd, rank // gd
+    first, count = shard.direction_shard(D, gd, dgrp)
+    per = shard.padded_count(D, gd)
+    f0, nf = shard.frame_shard(B, gf, fgrp)
+    nf_max = shard.frame_shard(B, gf, 0)[1]
+    if nf <= 0:
+        raise SystemExit(f"{B} frames do not fill {gf} frame groups")
+    T_loc = (nf - 1) * N + c["W"]                          # this rank's slice of the stream: frames f0 .. f0 + nf
 
     w = bflk.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"], device=local,
                         frame_len=N, history=c["H"], window_len=c["W"])
     w.set_kernel(args.kernel)
     w.set_direction_range(first, count)
 
-    host_in = torch.from_numpy(make_input(c, T)).pin_memory()
+    host_all = make_input(c, T)
+    host_in = torch.from_numpy(np.ascontiguousarray(host_all[:, f0 * N: f0 * N + T_loc])).pin_memory()
+    del host_all
     stream_dev = host_in.to(dev, non_blocking=True)
-    local_pow = torch.zeros((B, per), dtype=torch.float32, device=dev)
-    local_view = local_pow if count == per else None      # ragged shard: the kernel writes a [B][count] buffer
-    local_tight = local_pow if count == per else torch.empty((B, count), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world, B, per), dtype=torch.float32, device=dev) if world > 1 else None
+    local_pow = torch.zeros((nf_max, per), dtype=torch.float32, device=dev)
+    tight = count == per and nf == nf_max                  # ragged shard: the kernel writes a [nf][count] buffer
+    local_tight = local_pow if tight else torch.empty((nf, count), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, nf_max, per), dtype=torch.float32, device=dev) if world > 1 else None
     host_out = torch.empty((B, D), dtype=torch.float32).pin_memory()
+    in_group = None
+    if world > 1 and gd > 1 and gf > 1:                    # ranks that share a frame slice replicate its input among themselves
+        groups = [dist.new_group(list(range(g * gd, (g + 1) * gd))) for g in range(gf)]
+        in_group = groups[fgrp]
     torch.cuda.synchronize()
     # a real (non-null) stream: kernels, NCCL and the timing events all go on it
     work_stream = torch.cuda.Stream(device=dev)
@@ -260,11 +278,11 @@ def run_ours(args, c, name):
     assert cs != 0
 
     def step():
-        w.power_map_batch_dev(stream_dev.data_ptr(), T, B, local_tight.data_ptr(), cs)
+        w.power_map_batch_dev(stream_dev.data_ptr(), T_loc, nf, local_tight.data_ptr(), cs)
         if world > 1:
-            if local_view is None:
-                local_pow[:, :count].copy_(local_tight)
-            shard.gather_maps(local_pow, D, out=gathered)
+            if not tight:
+                local_pow[:nf, :count].copy_(local_tight)
+            dist.all_gather_into_tensor(gathered.view(world * nf_max, per), local_pow)
 
     def barrier():
         if world > 1:
@@ -310,15 +328,17 @@ def run_ours(args, c, name):
             def e2e_step():
                 w.power_map_batch_ptr(host_in.data_ptr(), T, B, host_out.data_ptr())
         else:
-            full = gathered
-
-            slice_dev = torch.empty((C // world, T), dtype=torch.float32, device=dev) if C % world == 0 else None
+            slice_dev = torch.empty((C // gd, T_loc), dtype=torch.float32, device=dev) if gd > 1 and C % gd == 0 else None
 
             def e2e_step():
-                # each rank uploads C / G channel rows over its own PCIe link, one NVLink all-gather replicates them
-                shard.replicate_input(host_in, stream_dev, staging=slice_dev)
+                # a frame group's ranks each upload C / G_d channel rows of its slice over their own PCIe link and one
+                # NVLink all-gather among them replicates the slice (G_d = 1: every rank uploads just its own frames)
+                if gd > 1:
+                    shard.replicate_input(host_in, stream_dev, group=in_group, staging=slice_dev)
+                else:
+                    stream_dev.copy_(host_in, non_blocking=True)
                 step()
-                host_out.copy_(shard.assemble(full, D), non_blocking=True)
+                host_out.copy_(shard.assemble_2d(gathered, B, D, gd, gf), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         e2e_steps = max(3, args.steps // 3)
         if world == 1:
@@ -331,12 +351,11 @@ def run_ours(args, c, name):
             ems = 1e3 * (time.perf_counter() - t0)
         else:
             ems = timed(e2e_step, e2e_steps, 1)
-        e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": C * T * 4,
+        e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": C * T_loc * 4 * gf,
                "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
                "path": "bflk_power_map_batch (host buffers)" if world == 1 else
-               "pinned H2D of C/G channel rows per rank + input all_gather + bflk_power_map_batch_dev + map all_gather + D2H"}
-        if world > 1:
-            e2e["h2d_bytes_per_step"] = C * T * 4        # summed over the ranks (each uploads 1 / G of it)
+               "pinned H2D of the rank's frame slice (C/G_d channel rows each + all_gather inside the frame group) + "
+               "bflk_power_map_batch_dev + map all_gather + D2H; h2d bytes summed over the ranks"}
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -345,10 +364,10 @@ def run_ours(args, c, name):
         max_mhz = pk.get("sm_max_mhz") or clocks["sm_max_mhz"] or 1965.0
         peak_tf = sm_count * FP32_LANES_PER_SM * 2 * max_mhz * 1e6 / 1e12
         # algorithmic FLOPs one das launch performs on this rank: B maps x per directions
-        fl = flops_per_map(C, count, N) * B
+        fl = flops_per_map(C, count, N) * nf
         das_avg_s = das_ms / 1e3 / max(1, das_n)
         achieved_tf = fl / das_avg_s / 1e12 if das_n else None
-        alg_bytes = 4 * C * T + 4 * B * count
+        alg_bytes = 4 * C * T_loc + 4 * nf * count
         roof = {"bound": "fp32", "kernel": {1: "das_generic", 2: "das_tile", 3: "das_bcast", 4: "das_tile_fma2"}.get(kinfo[0], "?"), "achieved": achieved_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if achieved_tf else None,
                 "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz {max_mhz:.0f} ({pk_kind} MEASURED_PEAKS.json clock)",
@@ -365,7 +384,8 @@ def run_ours(args, c, name):
         roof_hbm = {"bound": "hbm", "achieved": alg_bytes / das_avg_s / 1e9 if das_n else None, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
                     "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
-        cfg.update(parallelism=f"direction-sharded x{world}" if world > 1 else "single GPU", directions_per_gpu=count,
+        cfg.update(parallelism=f"{gd} direction groups x {gf} frame groups" if world > 1 else "single GPU", directions_per_gpu=count,
+                   frames_per_gpu=nf,
                    kernel=roof["kernel"], tile_span=kinfo[1], window_chunks=kinfo[2])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -84,6 +84,40 @@ def test_channel_sliced_upload_replicates_the_stream(tmp_path, world, C):
     assert np.all(np.load(out) == 1.0)
 
 
+def _grid2d_worker(rank, world, port, gd, B, D, out_path):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bflk import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gd, gf = shard.grid_2d(world, gd)
+    d0, dc = shard.direction_shard(D, gd, rank % gd)
+    f0, fc = shard.frame_shard(B, gf, rank // gd)
+    per, nf = shard.padded_count(D, gd), shard.frame_shard(B, gf, 0)[1]
+    truth = torch.arange(B * D, dtype=torch.float32).reshape(B, D)          # "map" value = its own flat index
+    local = torch.zeros((nf, per))
+    local[:fc, :dc] = truth[f0:f0 + fc, d0:d0 + dc]
+    out = torch.empty((world, nf, per))
+    dist.all_gather_into_tensor(out.view(world * nf, per), local)
+    full = shard.assemble_2d(out, B, D, gd, gf)
+    ok = torch.equal(full, truth)
+    flags = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([float(ok)]))
+    if rank == 0:
+        np.save(out_path, np.array([f.item() for f in flags]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,gd,B,D", [(4, 2, 8, 64), (4, 2, 10, 35), (2, 1, 6, 16), (3, 3, 4, 10)])
+def test_direction_by_frame_grid_assembles(tmp_path, world, gd, B, D):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_grid2d_worker, args=(world, _free_port(), gd, B, D, out), nprocs=world, join=True)
+    assert np.all(np.load(out) == 1.0)
+
+
 def test_direction_shard_partition():
     import sys
     if PKG not in sys.path:
