@@ -31,7 +31,7 @@ SYMBOLS = [
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
-    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev", "bflk_monopulse",
+    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
 ]
 
@@ -92,6 +92,7 @@ def load_library():
     L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.bflk_miso_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     L.bflk_monopulse.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
+    L.bflk_set_fir.argtypes = [vp, vp, i32, i32]
     L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
     L.bflk_calibrate.argtypes = [vp, vp, i32, f32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
     L.bflk_ingest_i32.argtypes = [vp, vp, i32, i32, vp]
@@ -277,6 +278,14 @@ class Beamformer:
         self._check(self._L.bflk_miso(self._h, _ptr(theta), _ptr(phi), T, _ptr(window),
                                       _ptr(audio) if want_audio else None, _ptr(power) if want_power else None))
         return audio, power
+
+    def set_fir(self, coeffs):
+        """FIR interpolation of the reference's USE_FILTER build (delay.cpp:28-40): coeffs [n_phases][taps], None = 2-tap form."""
+        if coeffs is None:
+            self._check(self._L.bflk_set_fir(self._h, None, 0, 0))
+            return
+        coeffs = _np(coeffs, np.float32)
+        self._check(self._L.bflk_set_fir(self._h, _ptr(coeffs), coeffs.shape[0], coeffs.shape[1]))
 
     def monopulse(self, theta, phi, window, spread, theta_limit, reference=0.0):
         """GradientParticle::findNearby + the beam part of step() for P particles: returns (theta' [P], near_theta [P][4],

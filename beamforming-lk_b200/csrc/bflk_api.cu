@@ -80,7 +80,7 @@ int bflk_destroy(bflk_handle *h) {
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
-    h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
+    h->d_fir.release(); h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release();
@@ -548,7 +548,11 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
     // automatic choice: register-tiled kernel when the grid tiles (2x2 direction tiles with small offset
     // spread), else the lane-broadcast kernel (any direction list), else the generic kernel (any frame length)
     bool tiled = false;
-    if (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4) {
+    const bool fir = h->fir_phases > 0;   // FIR interpolation runs through the generic kernel only
+    if (fir && h->kernel_choice > 1) return h->fail(BFLK_ERR_STATE, "bflk_power_map: FIR interpolation needs kernel 0 or 1");
+    if (fir && n_samples < min_stream_samples(h, n_frames) + h->fir_taps - 2)
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: the FIR reads %d samples past a frame's last tap", h->fir_taps - 2);
+    if (!fir && (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4)) {
         // automatic choice = the two-FMA variant (power within the 1e-4 bar); 2 asks for bit-identical delayed sums
         int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0);
         if (rc) return rc;
@@ -560,7 +564,7 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
     const bool bcast_ok = N >= 256;
     if (h->kernel_choice == 3 && !bcast_ok)
         return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256");
-    if (!tiled && (h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
+    if (!fir && !tiled && (h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
         int rc = ensure_bcast(h);
         if (rc) return rc;
         BcastArgs a{};
@@ -636,6 +640,7 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
         a.power = power_dev;
         a.audio = nullptr;
         a.norm = norm;
+        if (fir) { a.fir = h->d_fir.p; a.fir_phases = h->fir_phases; a.fir_taps = h->fir_taps; }
         timing_hook(h, 0, true, st);
         BFLK_CUDA(h, launch_das_generic(a, st));
         timing_hook(h, 0, false, st);
@@ -770,6 +775,11 @@ int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_
     a.power = power_dev;
     a.audio = audio_dev;
     a.norm = static_cast<float>(N);  // Particle::beam: power_accumulator /= N_SAMPLES, particle.cpp:79
+    if (h->fir_phases > 0) {
+        if (h->cfg.window_len < h->cfg.history + N + h->fir_taps - 1)
+            return h->fail(BFLK_ERR_INVALID, "bflk_miso: the window is too short for the FIR taps");
+        a.fir = h->d_fir.p; a.fir_phases = h->fir_phases; a.fir_taps = h->fir_taps;
+    }
     BFLK_CUDA(h, launch_das_generic(a, st));
     h->launches++;
     return BFLK_OK;
@@ -793,6 +803,23 @@ int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_
                                      cudaMemcpyDeviceToHost, h->stream));
     if (power_out) BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_targets * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+// ---- FIR interpolation mode ---------------------------------------------------------------------
+int bflk_set_fir(bflk_handle *h, const float *coeffs, int32_t n_phases, int32_t n_taps) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!coeffs) {
+        h->fir_phases = h->fir_taps = 0;
+        return BFLK_OK;
+    }
+    if (n_phases < 2 || n_taps < 1 || n_taps > 64) return h->fail(BFLK_ERR_INVALID, "bflk_set_fir: %d phases x %d taps", n_phases, n_taps);
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    BFLK_CUDA(h, h->d_fir.reserve((size_t)n_phases * n_taps));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_fir.p, coeffs, (size_t)n_phases * n_taps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->fir_phases = n_phases;
+    h->fir_taps = n_taps;
     return BFLK_OK;
 }
 

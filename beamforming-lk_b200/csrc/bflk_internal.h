@@ -175,6 +175,10 @@ struct bflk_handle {
     bflk::DevBuf<int32_t> d_bcast_dirs;            // [tile][32] local direction index or -1
     bflk::DevBuf<int32_t> d_bcast_globals;         // [tile][32] grid direction index or -1
 
+    // optional FIR interpolation (bflk_set_fir): coefficient table on the device
+    bflk::DevBuf<float> d_fir;
+    int32_t fir_phases = 0, fir_taps = 0;
+
     // scratch
     bflk::DevBuf<float> d_window, d_power, d_audio, d_partial;
     bflk::DevBuf<bflk::DirTrig> d_trig;
@@ -241,6 +245,8 @@ struct GenericArgs {
     float *power;          // [B][n_dir] or nullptr
     float *audio;          // [B][n_dir][N] or nullptr
     float norm;            // power divisor: N*count (MIMO) or N (beam)
+    const float *fir = nullptr;   // [fir_phases][fir_taps] coefficients: FIR interpolation instead of the 2-tap triple
+    int fir_phases = 0, fir_taps = 0;
 };
 cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st);
 

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArg
     const int b = blockIdx.y;
     const int N = a.frame_len;
     long long *s_addr = reinterpret_cast<long long *>(s_raw);
-    float *s_frac = reinterpret_cast<float *>(s_raw + sizeof(long long) * a.usable);
+    float *s_frac = reinterpret_cast<float *>(s_raw + sizeof(long long) * a.usable);   // FIR mode: the phase index, as int bits
     float *s_out = s_frac + a.usable;
     const int32_t *off = a.off + (size_t)d * a.C;
     const float *frac = a.frac + (size_t)d * a.C;
@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArg
     for (int s = threadIdx.x; s < a.usable; s += kGenericThreads) {
         const int c = a.index[s];
         s_addr[s] = (long long)c * a.row_stride + off[c];
-        s_frac[s] = frac[c];
+        if (a.fir)   // delay.cpp:30-31: float get_filter = fraction * 100.0f + 0.5f; int delay_int = (int) get_filter;
+            s_frac[s] = __int_as_float(min(a.fir_phases - 1, (int)__fadd_rn(__fmul_rn(frac[c], (float)(a.fir_phases - 1)), 0.5f)));
+        else
+            s_frac[s] = frac[c];
     }
     __syncthreads();
 
@@ -40,6 +43,16 @@ __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArg
         float acc = 0.0f;
         if (i < N) {
             const float *sig0 = base + i;
+            if (a.fir) {
+                // 8-tap fractional-delay FIR of the reference's USE_FILTER build (delay.cpp:33-37):
+                // out[n] += coeffs[phase][i] * signal[n + i], i = 0..taps-1 in order, each step one fma
+                for (int s = 0; s < a.usable; s++) {
+                    const float *sig = sig0 + s_addr[s];
+                    const float *cf = a.fir + (size_t)__float_as_int(s_frac[s]) * a.fir_taps;
+#pragma unroll 8
+                    for (int t = 0; t < a.fir_taps; t++) acc = __fmaf_rn(__ldg(cf + t), __ldg(sig + t), acc);
+                }
+            } else
 #pragma unroll 8
             for (int s = 0; s < a.usable; s++) {
                 const float *sig = sig0 + s_addr[s];

@@ -131,6 +131,13 @@ int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_
 int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets,
                   const float *window_dev, float *audio_dev, float *power_dev, void *cuda_stream);
 
+/* FIR fractional-delay interpolation instead of the 2-tap form: the reference's USE_FILTER build of delay()
+ * (src/dsp/delay.cpp:28-40; coefficient table src/dsp/filter.h, 101 phases x 8 taps -- reference data, supplied by the
+ * caller): phase = (int)(fraction * (n_phases - 1) + 0.5f), out[n] += coeffs[phase][i] * signal[n + i], i in order.
+ * While set, power maps and MISO calls run through the generic kernel and a frame reads n_taps - 2 more samples;
+ * coeffs = NULL restores the 2-tap form. */
+int bflk_set_fir(bflk_handle *h, const float *coeffs, int32_t n_phases, int32_t n_taps);
+
 /* Monopulse step of the gradient tracker (GradientParticle::findNearby + the beam part of GradientParticle::step,
  * quadrant form, src/dsp/gradient_ascend.cpp:18-81).  For each particle p: the four quadrant directions at angular
  * distance `spread` around (theta[p], phi[p]) (Spherical::quadrant, src/geometry/geometry.cpp:181-217 -- like the

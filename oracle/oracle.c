@@ -288,3 +288,31 @@ void orc_monopulse_gradient(const double *q, double reference, double *gradient,
     gradient[1] = reference > 0.0 ? phi / reference : phi;
     gradient[2] = sum / 4;
 }
+
+/* ---- f4: FIR fractional-delay variant of delay() (src/dsp/delay.cpp:28-40, USE_FILTER build) ---------------- */
+/* coeffs[n_phases][taps] is filter.h's table in the reference (101 x 8); the taps accumulate in order, one fma each
+ * (the reference build that would compile this is -Ofast: its contraction / order is not observable here). */
+void orc_delay_fir(float *out, const float *signal, float fraction, int n, const float *coeffs, int n_phases, int taps) {
+    float get_filter = fraction * (float)(n_phases - 1) + 0.5f;     /* fraction * 100.0f + 0.5f */
+    int delay_int = (int)get_filter;
+    if (delay_int > n_phases - 1) delay_int = n_phases - 1;
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < taps; i++) out[k] = fmaf(coeffs[(size_t)delay_int * taps + i], signal[k + i], out[k]);
+}
+
+void orc_mimo_update_fir(const float *window, int C, int W, int n, const int *index, int usable,
+                         const int32_t *offsets, const float *fractions, int D, const float *coeffs, int n_phases,
+                         int taps, float *power) {
+    float *out = (float *)malloc(sizeof(float) * n);
+    for (int m = 0; m < D; m++) {
+        memset(out, 0, sizeof(float) * n);
+        for (int s = 0; s < usable; s++) {
+            int i = index[s];
+            orc_delay_fir(out, &window[(size_t)i * W + offsets[(size_t)m * C + i]], fractions[(size_t)m * C + i], n, coeffs, n_phases, taps);
+        }
+        float p = hp_power(out, n);
+        p /= (float)(n * usable);
+        power[m] = p;
+    }
+    free(out);
+}

@@ -91,6 +91,12 @@ void orc_ingest(const int32_t *frames, int n, int n_sensors, float *exposure);
 void orc_quadrant(double *theta, double phi, double spread, double theta_limit, double *near_theta, double *near_phi);
 void orc_monopulse_gradient(const double *q, double reference, double *gradient, double *error);
 
+/* f4: FIR variant of delay() (delay.cpp:28-40) and the power map built on it */
+void orc_delay_fir(float *out, const float *signal, float fraction, int n, const float *coeffs, int n_phases, int taps);
+void orc_mimo_update_fir(const float *window, int C, int W, int n, const int *index, int usable,
+                         const int32_t *offsets, const float *fractions, int D, const float *coeffs, int n_phases,
+                         int taps, float *power);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,9 @@ def lib():
         L.orc_mimo_das.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, C.c_int, _f32p]
         L.orc_particle_beam.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, _f32p]
         L.orc_particle_beam.restype = C.c_double
+        L.orc_mimo_update_fir.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, C.c_int, _f32p,
+                                          C.c_int, C.c_int, _f32p]
+        L.orc_mimo_update_fir.restype = None
         L.orc_quadrant.argtypes = [_f64p, C.c_double, C.c_double, C.c_double, _f64p, _f64p]
         L.orc_quadrant.restype = None
         L.orc_monopulse_gradient.argtypes = [_f64p, C.c_double, _f64p, _f64p]
@@ -254,3 +257,16 @@ def monopulse(xyz, theta, phi, window, spread, theta_limit, reference=0.0, index
         lib().orc_monopulse_gradient(np.ascontiguousarray(q[p]), float(reference), grad[p], e)
         err[p] = e[0]
     return theta, nth, nph, q, grad, err
+
+
+def mimo_update_fir(window, offsets, fractions, coeffs, index=None, n=N_SAMPLES):
+    """MIMOWorker::update around the FIR variant of delay() (delay.cpp:28-40); coeffs [n_phases][taps]."""
+    window = np.ascontiguousarray(window, np.float32)
+    coeffs = np.ascontiguousarray(coeffs, np.float32)
+    Cn, W = window.shape
+    index = _idx(index, Cn)
+    D = offsets.shape[0]
+    power = np.zeros(D, np.float32)
+    lib().orc_mimo_update_fir(window, Cn, W, n, index, len(index), np.ascontiguousarray(offsets, np.int32),
+                              np.ascontiguousarray(fractions, np.float32), D, coeffs, coeffs.shape[0], coeffs.shape[1], power)
+    return power

@@ -266,6 +266,44 @@ def test_monopulse_step_vs_oracle(bf, oracle):
     assert g[0, 2] > 0 and np.all(q > 0)
 
 
+def _sinc_table(phases=101, taps=8):
+    """A windowed-sinc fractional-delay table of the reference's shape (filter.h: 101 phases x 8 taps); own coefficients.
+    Phase f delays by f like the 2-tap form does (out ~ s(n + 3 - f)), so both interpolators steer the same way."""
+    k = np.arange(taps)[None, :] - (taps // 2 - 1)
+    fr = np.linspace(0.0, 1.0, phases)[:, None]
+    h = np.sinc(k + fr) * np.hamming(taps + 2)[1:-1][None, :]
+    return (h / h.sum(axis=1, keepdims=True)).astype(np.float32)
+
+
+def test_fir_interpolation_mode_vs_oracle(bf, oracle):
+    """f4: the USE_FILTER variant of delay() (delay.cpp:28-40) through the generic kernel, caller's table."""
+    c = cases.CONFIGS["cfg2"]
+    w = bf.MIMOWorker(cases.origins(c["nx"], c["ny"]), 16, 12, 150.0)
+    window = _synth_window(bf, c)
+    coeffs = _sinc_table()
+    off, fr = w.tables()
+    p2 = w.update(window)
+    w.set_fir(coeffs)
+    p = w.update(window)
+    assert w.kernel_info()[0] == 1                                   # FIR runs through the generic kernel
+    po = oracle.mimo_update_fir(window, off, fr, coeffs)
+    assert rel_err(p, po) <= POWER_RTOL and int(np.argmax(p)) == int(np.argmax(po))
+    assert rel_err(p, p2) > 1e-3                                     # a different interpolator ...
+    ra, ca = divmod(int(np.argmax(p)), 12)                           # ... that sees the same scene: peak within a cell
+    rb, cb = divmod(int(np.argmax(p2)), 12)
+    assert abs(ra - rb) <= 1 and abs(ca - cb) <= 1
+    mask = np.arange(0, 256, 3, dtype=np.int32)
+    w.set_channel_mask(mask)
+    assert rel_err(w.update(window), oracle.mimo_update_fir(window, off, fr, coeffs, index=mask)) <= POWER_RTOL
+    w.set_kernel(4)
+    with pytest.raises(bf.BflkError):
+        w.update(window)                                             # the tiled kernels have no FIR form
+    w.set_kernel(0)
+    w.set_fir(None)
+    w.set_channel_mask(np.arange(256, dtype=np.int32))
+    assert np.array_equal(w.update(window), p2)                      # back to the 2-tap form, same bits
+
+
 # ---- batching, sharding, masks, edge cases -----------------------------------------------------------------------
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_batch_equals_single_frames(bf, oracle, kernel):
