@@ -27,6 +27,11 @@ K = 8
 VOTE = os.environ.get("BFLK_GEN_VOTE", "0") == "1"
 BRX = os.environ.get("BFLK_GEN_BRX", "0") == "1"
 CHAIN = os.environ.get("BFLK_GEN_CHAIN", "1") == "1"
+# two-FMA variants: next channel's window loads issued INSIDE the last direction's body, each chunk right after the last
+# FFMA2 that reads the registers it lands in (no extra registers, the load latency hides behind the rest of the body)
+# Measured: single-window flavour cfg5 0.588 -> 0.595, cfg1 +-0; two-window flavour cfg3 0.560 -> 0.522, cfg2 0.595 -> 0.559
+# (shared memory is already 81 % busy there; earlier loads only lengthen its queue) -> "single"
+PIPE_MODE = os.environ.get("BFLK_GEN_PIPE", "single")
 # two-FMA variants: one loop tail (fraction prefetch, next window addresses, loop branch) shared by all last-direction
 # bodies instead of a copy per body.  ptxas then coalesces the accumulators across the back edge (26 -> 8 MOVs in the
 # two-window loop); measured +0.3 .. +0.5 % for the two-window flavour, -1.5 % for the single-window one -> "dual"
@@ -343,6 +348,7 @@ def gen_fast(nch, dual=False):
     esz = 80 if dual else 64
     o_dl, o_f, o_g = (64, 32, 48) if dual else (16, 32, 48)
     shared_tail = SHARED_TAIL == "1" or (SHARED_TAIL == "dual" and dual)
+    PIPE = PIPE_MODE == "1" or (PIPE_MODE == "single" and not dual)
     L = []
     emit = L.append
 
@@ -375,10 +381,14 @@ def gen_fast(nch, dual=False):
         emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+{o_f}];")
         emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+{o_g}];")
 
+    prologue = [True]
+
     def entry_tail():
-        """addresses of the next window A, first direction's predicates"""
-        for c in range(4):
-            emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+        """addresses of the next window A (pipelined variant: formed at the start of B3 instead), first direction's predicates"""
+        if prologue[0] or not PIPE:
+            for c in range(4):
+                emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+        prologue[0] = False
         preds(0)
 
     def subtree(r, lo, bit, tag):
@@ -419,12 +429,45 @@ def gen_fast(nch, dual=False):
     if os.environ.get("BFLK_GEN_EXP") == "nolds":
         window("oa")
         first_window[0] = False
+    if PIPE:
+        window("oa")          # first channel of the stage; later ones are loaded from inside the previous B3 body
     emit("TOP:")
-    window("oa")
+    if not PIPE:
+        window("oa")
     for r in range(4):
         emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
         emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
     tree_from(0, 0)
+
+    def body_recycling(r, D):
+        """body(r, D) in an order that frees window registers early (g0 g1 g2 g3 | f0 g4 | f1 g5 | f2 g6 | f3 g7 | f4..f7:
+        a dependent pair is never closer than four FFMA2), with the next channel's window chunk m loaded (if the stage
+        goes on) as soon as both registers of the chunk have been read for the last time."""
+        g = lambda k: f"    fma.rn.f32x2 {A(r, k)}, gg{r}, w{D + k + 1}, {A(r, k)};"
+        f = lambda k: f"    fma.rn.f32x2 {A(r, k)}, ff{r}, w{D + k}, {A(r, k)};"
+        order = [("g", 0), ("g", 1), ("g", 2), ("g", 3)]
+        for k in range(4):
+            order += [("f", k), ("g", k + 4)]
+        order += [("f", k) for k in range(4, 8)]
+        last_use = {}
+        for pos, (kind, k) in enumerate(order):
+            last_use[D + k + (1 if kind == "g" else 0)] = pos
+        loaded = set()
+
+        def issue_free(pos):
+            for m in range(nch):
+                if m in loaded:
+                    continue
+                if all(last_use.get(j, -1) <= pos for j in (2 * m, 2 * m + 1)):
+                    loaded.add(m)
+                    emit(f"    @ploop ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [oa{m & 3}+{16 * (m + (m >> 2))}];")
+
+        issue_free(-1)
+        for pos, (kind, k) in enumerate(order):
+            emit(g(k) if kind == "g" else f(k))
+            issue_free(pos)
+        assert len(loaded) == nch
+
     for dd in range(kmax + 1):
         for r in range(4):
             emit(f"B{r}_{dd}:")
@@ -449,13 +492,23 @@ def gen_fast(nch, dual=False):
                 tree_from(2, dd)
             elif r == 2:
                 preds(3)
+                if PIPE:
+                    # the next channel's entry head already here: its window addresses are needed inside B3
+                    emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+                    load_entry_head()
+                    emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
                 body(r, dd)
                 tree_from(3, dd)
             else:
-                emit(f"    add.u32 {ENT}, {ENT}, {esz};")
-                load_entry_head()
-                emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
-                body(r, dd)
+                if PIPE:
+                    for c in range(4):
+                        emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+                    body_recycling(r, dd)
+                else:
+                    emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+                    load_entry_head()
+                    emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
+                    body(r, dd)
                 if shared_tail:
                     emit("    bra.uni TAIL;")
                 else:
