@@ -131,3 +131,38 @@ def test_direction_shard_partition():
                 assert f0 + c0 == f1
             assert max(c for _, c in runs) == shard.padded_count(D, world)
             assert max(c for _, c in runs) - min(c for _, c in runs) <= 1
+
+
+def test_frame_groups_and_bench_batch_rule():
+    """Host logic of the direction x frame decomposition and of bench.py's default batch: frame slices are even-sized,
+    contiguous and cover the batch; the default batch makes the block pairs a multiple of 148 SMs (whole CTA waves at
+    1, 2, 4 and 8 GPUs) and is larger than L2."""
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from bflk import shard
+    import bench
+    assert shard.grid_2d(1) == (1, 1) and shard.grid_2d(2) == (2, 1) and shard.grid_2d(8) == (2, 4)
+    assert shard.grid_2d(8, 8) == (8, 1) and shard.grid_2d(8, 1) == (1, 8) and shard.grid_2d(3) == (1, 3)
+    with pytest.raises(ValueError):
+        shard.grid_2d(8, 3)
+    for B in (2, 7, 592, 593, 4144):
+        for groups in (1, 2, 3, 4, 8):
+            runs = [shard.frame_shard(B, groups, g) for g in range(groups)]
+            assert runs[0][0] == 0 and sum(c for _, c in runs) == B
+            for (f0, c0), (f1, c1) in zip(runs, runs[1:]):
+                assert f0 + c0 == f1 or c1 == 0
+            nonempty = [c for _, c in runs if c]
+            assert all(c % 2 == 0 for c in nonempty[:-1]) and runs[0][1] == max(nonempty)   # only the last slice may be odd
+    for name in ("cfg1", "cfg2", "cfg3"):
+        c = cases.CONFIGS[name]
+        B = bench.default_frames(c)
+        assert (B // 2) % 148 == 0 and B % 2 == 0
+        assert 64 * c["nx"] * c["ny"] * B * c["N"] * 4 >= 256e6          # input larger than L2 (126 MB)
+    assert bench.default_frames(cases.CONFIGS["cfg3"]) == 592
+    for world in (2, 4, 8):                                               # every rank gets whole waves at cfg3
+        gd, gf = shard.grid_2d(world)
+        nf = shard.frame_shard(592, gf, 0)[1]
+        ctas = (nf // 2) * -(-(1024 // gd // 4) // 16)
+        assert ctas % 148 == 0
