@@ -12,11 +12,15 @@
 //    per-thread windows becomes 80 bytes, which is bank-conflict-free for LDS.128.
 //  * das_tile_kernel: one warp = one 2x2 tile of steering directions x two 256-sample blocks; lane l
 //    owns output samples 8l..8l+7 of both blocks.  Per channel the warp loads ONE shared window of
-//    sample pairs into registers, forms the differences s[i]-s[i+1] once, and serves the four
-//    directions from registers through a warp-uniform switch on each direction's offset inside the
-//    window: 2 + 1/4 FP32 lane-operations per (direction, channel, sample) instead of 3, and ~0.4
-//    shared-memory words instead of >1.  Channels are accumulated sequentially in mask order with the
-//    reference's exact operation triple, so the delayed sums are bit-identical to the CPU path.
+//    sample pairs into registers (or one per direction pair on coarse grids) and serves the four
+//    directions from registers through a warp-uniform dispatch on each direction's offset inside the
+//    window.  Two accumulate forms:
+//      - exact triple (kernel 2): differences s[i]-s[i+1] formed once per window, then
+//        acc = acc + fma(f, d, s[i+1]) per direction in mask order -- delayed sums bit-identical to
+//        delay(); 2 + 1/4 FP32 lane-operations per (direction, channel, sample);
+//      - two-FMA form (kernel 4, automatic; template parameter FAST): acc = fma(f, s[i], fma(g, s[i+1], acc)),
+//        g = 1 - f from the table -- 16 FFMA2 per (direction, channel) and nothing else on the FP pipe,
+//        the whole pipeline stage in one generated PTX block (das_tile_fast_asm.inc).
 //  * epilogue: 3-tap high-pass + squares (mimo.cpp:131-135) with neighbour samples from lane +-1,
 //    warp-shuffle reduction, one store per (block, direction).
 #include <algorithm>
