@@ -670,7 +670,8 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
     // Chunks of frames: the H2D copy of chunk k+1 (copy_stream) overlaps the kernels of chunk k (stream).
     // A chunk is ~32 MiB of new samples, rounded to whole CTA waves, so PCIe and the SMs both stay busy; small batches
     // are one chunk.
-    const int64_t tail = min_stream_samples(h, 1) - N;  // samples a frame needs beyond its own N
+    // samples a frame needs beyond its own N (the FIR interpolation reads taps - 2 more)
+    const int64_t tail = min_stream_samples(h, 1) - N + (h->fir_phases > 0 ? h->fir_taps - 2 : 0);
     int64_t chunk_bytes = 32ll << 20;  // measured on B200 / PCIe 5 at cfg3 with wave-aligned chunks: 32 MiB 64.7 k maps/s, 64 MiB 61.6 k, 96 MiB 56.9 k
     if (const char *env = getenv("BFLK_CHUNK_MIB")) chunk_bytes = std::max(1, atoi(env)) * (1ll << 20);  // tuning knob
     const int64_t frame_bytes = (int64_t)C * N * sizeof(float);
