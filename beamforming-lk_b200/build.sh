@@ -6,13 +6,23 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-ffp-contract=off ${EXTRA_NVCC_FLAGS:-}"
 mkdir -p build
 objs=()
-for f in csrc/bflk_api.cu csrc/tables.cu csrc/das_generic.cu csrc/das_tile.cu csrc/das_bcast.cu csrc/post.cu; do
+pids=()
+for f in csrc/*.cu; do
   o=build/$(basename "${f%.cu}").o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/bflk_internal.h -nt "$o" ] || [ csrc/das_common.cuh -nt "$o" ] || [ csrc/das_tile_asm.inc -nt "$o" ] || [ csrc/das_tile_fast_asm.inc -nt "$o" ] || [ ../include/bflk.h -nt "$o" ]; then
+  stale=0
+  [ -f "$o" ] || stale=1
+  for dep in "$f" csrc/*.h csrc/*.cuh csrc/*.inc ../include/bflk.h build.sh; do
+    [ "$dep" -nt "$o" ] && stale=1
+  done
+  if [ $stale = 1 ]; then
+    rm -f "$o"                      # a failed compile must not leave an older object for the link step
     $NVCC $FLAGS -c "$f" -o "$o" &
+    pids+=($!)
   fi
   objs+=("$o")
 done
-wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libbflk.so "${objs[@]}"
+for p in "${pids[@]:-}"; do
+  [ -n "$p" ] && { wait "$p" || { echo "build.sh: a compile failed" >&2; exit 1; }; }
+done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libbflk.so "${objs[@]}" -ldl
 echo "built $(pwd)/libbflk.so"

@@ -35,8 +35,6 @@ namespace {
 
 constexpr int kCC = kTileCC;         // channels per pipeline stage
 constexpr int kMaxStages = 4;        // stage buffers (KernelArgs::stages: 4 when shared memory allows, else 3)
-constexpr int kAhead = 2;            // stages in flight ahead of the consumers; with 4 buffers the producer thread refills
-                                     // the buffer every warp left TWO stages ago, so it never waits for a slow warp
 constexpr int kBlock = 256;          // output samples per block
 constexpr int kK = 8;                // sample pairs per lane
 constexpr int kFastMaxNch16 = 10;    // largest window of the two-FMA variant that still runs 16 warps per CTA
@@ -133,7 +131,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     const int stage_bytes = stage_rows + kWarps * kCC * kEnt;
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const int kStages = a.stages;
-    const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages], empty[kStages]
+    const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages] mbarriers, then done[kStages] arrival counters
+    unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + kStages * stage_bytes + 8 * kStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_stage = (a.usable + kCC - 1) / kCC;
@@ -141,22 +140,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     const int my_tile = min(tile0 + warp, a.n_tiles - 1);
     const bool active = tile0 + warp < a.n_tiles;  // idle warps of the last tile group only keep the pipeline moving
     // this CTA works on block pairs [pair_lo, pair_hi) one after the other; the staging pipeline runs straight through
-    // the pair boundaries (global stage counter gs), so the next pair's first stages load while this pair's epilogue runs
+    // the pair boundaries, so the next pair's first stages load while this pair's epilogue runs
     const int pair_lo = a.pair0 + blockIdx.y * a.pairs_per_cta;
     const int pair_hi = min(pair_lo + a.pairs_per_cta, a.pair0 + a.n_pairs);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (kStages + s), kWarps);
+            done_cnt[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int total_stages = n_stage * (pair_hi - pair_lo);
-    auto issue = [&](int g, int buf) {  // producer: one thread fills buffer buf = g % stages with global stage g = (pair, channel chunk)
-        const int pair = pair_lo + g / n_stage, st = g % n_stage;
+    // producer: fills buffer buf with (block pair `pair`, channel chunk `st`).  There is no producer warp and no "empty"
+    // barrier anybody waits on: the LAST warp to finish a stage (arrival counter in shared memory) refills the buffer it
+    // just freed with the stage kStages ahead, so no warp ever waits for a slower one and the prefetch distance is the
+    // whole ring.
+    auto issue = [&](int pair, int st, int buf) {
         const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
         const uint32_t dst = smem + buf * stage_bytes;
         const uint32_t full = bars + 8 * buf;
@@ -165,13 +166,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         bulk_g2s(dst, a.packed + ((size_t)pair * a.usable + c0) * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
         bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC) * kEnt, tile_bytes, full);
     };
-    if (threadIdx.x == 0)
-        for (int g = 0; g < min(kAhead, total_stages); g++) issue(g, g);
+    // (pair, chunk) of the stage kStages ahead of the one being consumed, advanced once per stage by every warp
+    int npair = pair_lo, nst = 0;
+    for (int g = 0; g < kStages; g++) {
+        if (threadIdx.x == 0 && npair < pair_hi) issue(npair, nst, g);
+        if (++nst == n_stage) { nst = 0; npair++; }
+    }
 
     const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
-    int gs = 0;                            // stages consumed so far by this CTA
-    int buf = 0, ph = 0;                   // buffer and barrier parity of stage gs
-    int pbuf = kAhead, pround = 0;         // buffer of stage gs + kAhead, parity of its round through the buffers
+    int buf = 0, ph = 0;                   // buffer and barrier parity of the stage being consumed
     for (int pair = pair_lo; pair < pair_hi; pair++) {
     u64 acc[4][kK];
 #pragma unroll
@@ -179,12 +182,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
 #pragma unroll
         for (int k = 0; k < kK; k++) acc[r][k] = 0ull;
 
-    for (int st = 0; st < n_stage; st++, gs++) {
-        // refill the buffer every warp left stages - kAhead stages ago with the chunk kAhead stages ahead
-        if (threadIdx.x == 0 && gs + kAhead < total_stages) {
-            if (gs + kAhead >= kStages) mbar_wait(bars + 8 * (kStages + pbuf), pround ^ 1);
-            issue(gs + kAhead, pbuf);
-        }
+    for (int st = 0; st < n_stage; st++) {
         mbar_wait(bars + 8 * buf, ph);
         const uint32_t rows_s = smem + buf * stage_bytes;
         const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * kEnt;
@@ -214,9 +212,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 8 * (kStages + buf));
+        if (lane == 0) {
+            // all of this warp's reads of the buffer have completed (their values were consumed above)
+            if (atomicInc(&done_cnt[buf], kWarps - 1) == kWarps - 1 && npair < pair_hi) issue(npair, nst, buf);
+        }
+        if (++nst == n_stage) { nst = 0; npair++; }
         if (++buf == kStages) { buf = 0; ph ^= 1; }
-        if (++pbuf == kStages) { pbuf = 0; pround ^= 1; }
     }
 
     // ---- epilogue: MA = 0.5 out[j] - 0.25 (out[j+1] + out[j-1]); power = sum MA^2 (mimo.cpp:131-137) ----
@@ -361,7 +362,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     const size_t ent_bytes = das_tile_entry_bytes(a.geom);
     // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
     int stages = kMaxStages;
-    auto smem_for = [&](int n) { return (size_t)n * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + 2 * n * 8 + 96; };
+    auto smem_for = [&](int n) { return (size_t)n * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + n * (8 + 4) + 96; };
     if (const char *env = getenv("BFLK_TILE_STAGES")) stages = atoi(env) == 3 ? 3 : 4;  // tuning knob
     if (smem_for(stages) > 227 * 1024) stages = 3;
     const size_t smem = smem_for(stages);

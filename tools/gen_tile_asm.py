@@ -27,6 +27,8 @@ K = 8
 VOTE = os.environ.get("BFLK_GEN_VOTE", "0") == "1"
 BRX = os.environ.get("BFLK_GEN_BRX", "0") == "1"
 CHAIN = os.environ.get("BFLK_GEN_CHAIN", "1") == "1"
+# exact-triple bodies: FADD2 / FSUB2 written as FFMA2 with a unit multiplier (same single rounding, one pipe)
+ADD_AS_FMA = os.environ.get("BFLK_GEN_ADD_AS_FMA", "0") == "1"
 # two-FMA variants: next channel's window loads issued INSIDE the last direction's body, each chunk right after the last
 # FFMA2 that reads the registers it lands in (no extra registers, the load latency hides behind the rest of the body)
 # Measured: single-window flavour cfg5 0.588 -> 0.595, cfg1 +-0; two-window flavour cfg3 0.560 -> 0.522, cfg2 0.595 -> 0.559
@@ -36,6 +38,8 @@ PIPE_MODE = os.environ.get("BFLK_GEN_PIPE", "single")
 # bodies instead of a copy per body.  ptxas then coalesces the accumulators across the back edge (26 -> 8 MOVs in the
 # two-window loop); measured +0.3 .. +0.5 % for the two-window flavour, -1.5 % for the single-window one -> "dual"
 SHARED_TAIL = os.environ.get("BFLK_GEN_SHARED_TAIL", "dual")
+# wide flavour (gen_wide): next channel's window loads from inside the last body (same idea as PIPE_MODE)
+PIPE_MODE_WIDE = os.environ.get("BFLK_GEN_PIPE_WIDE", "0")
 
 # operand numbers of the asm block: acc[4][8] "+l" 0..31, e0 32, e1 33 ("+r"), f0..f3 34..37 ("+f"),
 # row 38 ("r": shared address of this lane's row start), nxt 39 ("r": shared address of the next entry)
@@ -58,7 +62,10 @@ def gen(nch):
     def body(r, D):
         """acc[r][k] = acc[r][k] + fma(f, d[D+k], w[D+k+1]), k = 0..7  (delay.cpp:24), pipelined."""
         fma = lambda t, k: emit(f"    fma.rn.f32x2 t{t}, ff, d{D + k}, w{D + k + 1};")
-        add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
+        if ADD_AS_FMA:   # acc = fma(t, 1, acc): the same single rounding as the add, FFMA2 only on the FP pipe
+            add = lambda k, t: emit(f"    fma.rn.f32x2 {A(r, k)}, t{t}, one, {A(r, k)};")
+        else:
+            add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
         for k in range(depth):
             fma(k, k)
         for k in range(K):
@@ -85,6 +92,10 @@ def gen(nch):
     emit(f"    .reg .pred pa<{nbits}>, pb<{nbits}>, q<4>;")
     emit("    .reg .b32 x, rr, a<4>;")
     emit(f"    .reg .b64 ff, t<{depth}>, w<{nw}>, d<{nd}>;")
+    if ADD_AS_FMA:
+        emit("    .reg .b64 one, mone;")
+        emit("    mov.b64 one, 0x3F8000003F800000;")
+        emit("    mov.b64 mone, 0xBF800000BF800000;")
     # ---- window: chunk m sits at padded chunk m + ((r + m) >> 2), r = bits 24-25 of e1 -----------------
     emit(f"    add.u32 a0, {ROW}, {E0};")
     emit(f"    shr.u32 rr, {E1}, 24;")
@@ -100,7 +111,10 @@ def gen(nch):
     else:
         preds(0, sets[0])
     for j in range(nd):
-        emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")       # s[i] - s[i+1], once per window
+        if ADD_AS_FMA:
+            emit(f"    fma.rn.f32x2 d{j}, w{j + 1}, mone, w{j};")   # s[i] - s[i+1] = fma(s[i+1], -1, s[i])
+        else:
+            emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")       # s[i] - s[i+1], once per window
 
     if chain:
         uid = [0]
@@ -209,7 +223,10 @@ def gen_dual(nch):
 
     def body(r, D):
         fma = lambda t, k: emit(f"    fma.rn.f32x2 t{t}, ff, d{D + k}, w{D + k + 1};")
-        add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
+        if ADD_AS_FMA:   # acc = fma(t, 1, acc): the same single rounding as the add, FFMA2 only on the FP pipe
+            add = lambda k, t: emit(f"    fma.rn.f32x2 {A(r, k)}, t{t}, one, {A(r, k)};")
+        else:
+            add = lambda k, t: emit(f"    add.rn.f32x2 {A(r, k)}, {A(r, k)}, t{t};")
         for k in range(depth):
             fma(k, k)
         for k in range(K):
@@ -242,7 +259,10 @@ def gen_dual(nch):
 
     def subs():
         for j in range(nd):
-            emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")
+            if ADD_AS_FMA:
+                emit(f"    fma.rn.f32x2 d{j}, w{j + 1}, mone, w{j};")
+            else:
+                emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")
 
     uid = [0]
 
@@ -265,6 +285,10 @@ def gen_dual(nch):
     emit(f"    .reg .pred pa<{nbits}>, pb<{nbits}>, q<4>;")
     emit("    .reg .b32 x, rr, a<4>;")
     emit(f"    .reg .b64 ff, t<{depth}>, w<{nw}>, d<{nd}>;")
+    if ADD_AS_FMA:
+        emit("    .reg .b64 one, mone;")
+        emit("    mov.b64 one, 0x3F8000003F800000;")
+        emit("    mov.b64 mone, 0xBF800000BF800000;")
     window(0)
     preds(0, sets[0])
     preds(1, sets[1])
@@ -542,6 +566,203 @@ __device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[4][{K}], uint32_t ent, 
 """
 
 
+
+def gen_wide(nch, exact=False):
+    """Wide flavour for coarse grids: ONE direction pair per warp, lane l owns 16 consecutive sample pairs (a 512-sample block
+    per slot of the block pair), one window of 2*nch pairs shared by the two directions.  Per (warp, channel): 64 FFMA2 behind
+    TWO dispatches (32 FFMA2 each) and nch window loads -- half the dispatch and table traffic per FLOP of the 2x2 tile, which
+    on coarse grids (cfg3: a 2x2 tile spreads over up to 9 samples) needs two windows and four dispatches for the same work.
+    Packed rows carry one 16-byte pad per EIGHT chunks (lane stride 9 chunks = 144 B: bank-conflict free for LDS.128), so a
+    window chunk m sits at padded chunk m + ((r + m) >> 3), r = (first chunk) & 7: eight pad classes, offsets from the table.
+    entry (48 B): o[8] | dl, f0, f1, -   (g = 1 - f formed here with the table builder's rounding: sub.rn.f32)
+    exact=True: the reference's operation triple (differences once per window, fma + add per direction).
+    operands: acc[2][16] "+l" 0..31, ent 32 "+r", row 33 "r" (lane base inside the stage's rows), end 34 "r"."""
+    KW = 16
+    nw = 2 * nch
+    kmax = nw - (KW + 1)
+    assert kmax >= 0
+    nbits = max(1, kmax.bit_length())
+    ENT, ROWR, END = "%32", "%33", "%34"
+    esz = 48
+    PIPE = PIPE_MODE_WIDE == "1" and not exact
+    AW = lambda r, k: f"%{r * KW + k}"
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        if exact:
+            # acc = acc + fma(f, s[i] - s[i+1], s[i+1]) (delay.cpp:24), FFMA2 -> FADD2 software-pipelined 8 deep
+            depth = 8
+            fma = lambda t, k: emit(f"    fma.rn.f32x2 t{t}, ff{r}, d{D + k}, w{D + k + 1};")
+            if ADD_AS_FMA:   # acc = fma(t, 1, acc): the same single rounding as the add, on the FFMA2 path only
+                add = lambda k, t: emit(f"    fma.rn.f32x2 {AW(r, k)}, t{t}, one, {AW(r, k)};")
+            else:
+                add = lambda k, t: emit(f"    add.rn.f32x2 {AW(r, k)}, {AW(r, k)}, t{t};")
+            for k in range(depth):
+                fma(k, k)
+            for k in range(KW):
+                add(k, k % depth)
+                if k + depth < KW:
+                    fma(k % depth, k + depth)
+            return
+        for k in range(KW):
+            emit(f"    fma.rn.f32x2 {AW(r, k)}, gg{r}, w{D + k + 1}, {AW(r, k)};")
+        for k in range(KW):
+            emit(f"    fma.rn.f32x2 {AW(r, k)}, ff{r}, w{D + k}, {AW(r, k)};")
+
+    def preds(r):
+        for b in range(nbits):
+            emit(f"    and.b32 x, dl, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 p{b}, x, 0;")
+
+    def window(pred=""):
+        for m in range(nch):
+            emit(f"    {pred}ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [oa{m & 7}+{16 * (m + (m >> 3))}];")
+
+    def subs():
+        for j in range(nw - 1):
+            if ADD_AS_FMA:   # s[i] - s[i+1] = fma(s[i+1], -1, s[i]): one rounding, same result
+                emit(f"    fma.rn.f32x2 d{j}, w{j + 1}, mone, w{j};")
+            else:
+                emit(f"    sub.rn.f32x2 d{j}, w{j}, w{j + 1};")
+
+    def load_entry_head():
+        emit(f"    ld.shared.v4.u32 {{oa0, oa1, oa2, oa3}}, [{ENT}];")
+        emit(f"    ld.shared.v4.u32 {{oa4, oa5, oa6, oa7}}, [{ENT}+16];")
+
+    def load_entry_fracs():
+        emit(f"    ld.shared.v4.b32 {{dl, fb0, fb1, x}}, [{ENT}+32];")
+        for r in range(2):
+            emit(f"    mov.b32 f{r}, fb{r};")
+            if not exact:
+                emit(f"    sub.rn.f32 g{r}, 0f3F800000, f{r};")
+
+    def add_row():
+        for c in range(8):
+            emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+
+    def subtree(r, lo, bit, tag):
+        if bit < 0:
+            emit(f"    bra.uni B{r}_{lo};")
+            return
+        hi = lo + (1 << bit)
+        if hi > kmax:
+            subtree(r, lo, bit - 1, tag)
+            return
+        lab = f"T{tag}_{hi}_{bit}"
+        emit(f"    @p{bit} bra.uni {lab};")
+        subtree(r, lo, bit - 1, tag)
+        emit(f"{lab}:")
+        subtree(r, hi, bit - 1, tag)
+
+    need = set()
+
+    def tree_from(r, dd):
+        for b in reversed(range(nbits)):
+            want = (dd >> b) & 1
+            base = ((dd >> (b + 1)) << (b + 1)) | ((1 - want) << b)
+            if base > kmax:
+                continue
+            need.add((r, base, b))
+            emit(f"    @{'!' if want else ''}p{b} bra.uni S{r}_{base}_{b};")
+
+    def body_recycling(r, D):
+        """two-FMA body in an order that frees window registers early; the next channel's window chunk m is loaded (if the
+        stage goes on) as soon as both its registers have been read for the last time"""
+        g = lambda k: f"    fma.rn.f32x2 {AW(r, k)}, gg{r}, w{D + k + 1}, {AW(r, k)};"
+        f = lambda k: f"    fma.rn.f32x2 {AW(r, k)}, ff{r}, w{D + k}, {AW(r, k)};"
+        order = [("g", 0), ("g", 1), ("g", 2), ("g", 3)]
+        for k in range(KW - 4):
+            order += [("f", k), ("g", k + 4)]
+        order += [("f", k) for k in range(KW - 4, KW)]
+        last_use = {}
+        for pos, (kind, k) in enumerate(order):
+            last_use[D + k + (1 if kind == "g" else 0)] = pos
+        loaded = set()
+
+        def issue_free(pos):
+            for m in range(nch):
+                if m in loaded:
+                    continue
+                if all(last_use.get(j, -1) <= pos for j in (2 * m, 2 * m + 1)):
+                    loaded.add(m)
+                    emit(f"    @ploop ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [oa{m & 7}+{16 * (m + (m >> 3))}];")
+
+        issue_free(-1)
+        for pos, (kind, k) in enumerate(order):
+            emit(g(k) if kind == "g" else f(k))
+            issue_free(pos)
+        assert len(loaded) == nch
+
+    emit("{")
+    emit(f"    .reg .pred p<{nbits}>, ploop;")
+    emit("    .reg .b32 x, dl, fb<2>, oa<8>;")
+    emit("    .reg .f32 f<2>, g<2>;")
+    emit(f"    .reg .b64 ff<2>, gg<2>, w<{nw}>" + (f", d<{nw - 1}>, t<8>, one, mone;" if exact else ";"))
+    if exact and ADD_AS_FMA:
+        emit("    mov.b64 one, 0x3F8000003F800000;")
+        emit("    mov.b64 mone, 0xBF800000BF800000;")
+    load_entry_head()
+    load_entry_fracs()
+    add_row()
+    preds(0)
+    if PIPE:
+        window()
+    emit("TOP:")
+    if not PIPE:
+        window()
+    for r in range(2):
+        emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
+        if not exact:
+            emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
+    if exact:
+        subs()
+    tree_from(0, 0)
+    for dd in range(kmax + 1):
+        emit(f"B0_{dd}:")
+        preds(1)
+        # the next channel's entry head already here: the window addresses must be ready before the last body ends
+        emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+        if PIPE:
+            load_entry_head()
+        emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
+        body(0, dd)
+        tree_from(1, dd)
+        emit(f"B1_{dd}:")
+        if PIPE:
+            add_row()
+            body_recycling(1, dd)
+        else:
+            load_entry_head()
+            body(1, dd)
+        emit("    bra.uni TAIL;")
+    emit("TAIL:")
+    load_entry_fracs()
+    if not PIPE:
+        add_row()
+    preds(0)
+    emit("    @ploop bra.uni TOP;")
+    emit("    bra.uni DONE;")
+    for (r, base, b) in sorted(need):
+        emit(f"S{r}_{base}_{b}:")
+        subtree(r, base, b - 1, f"{r}_{base}_{b}")
+    emit("DONE:")
+    emit("}")
+    asm = "\n".join(f'        "{ln}\\n"' for ln in L)
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(2) for k in range(KW)] + ['"+r"(ent)'])
+    name = "tile_stage_wide_exact" if exact else "tile_stage_wide"
+    return f"""// NCH = {nch}: direction pair, 16 sample pairs per lane, window of {nw} sample pairs, deltas 0..{kmax}{', exact triple' if exact else ''}
+template <>
+__device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[2][{KW}], uint32_t ent, uint32_t row, uint32_t end) {{
+    asm volatile(
+{asm}
+        : {outs}
+        : "r"(row), "r"(end)
+        : "memory");
+}}
+"""
+
+
 # Measured and rejected: a double-buffered flavour (window B of a channel in flight to a second register set while slots
 # 0,1 run on window A, then window A of the next channel while slots 2,3 run): ~165 registers -> 12 warps per CTA (the
 # register file is split per scheduler, so 14 warps still cap a thread at 128), always two window loads per channel ->
@@ -561,6 +782,19 @@ __device__ __forceinline__ void tile_stage_fast_dual(u64 (&acc)[4][8], uint32_t 
         print(gen_fast(nch))
     for nch in (6, 7):
         print(gen_fast(nch, dual=True))
+    sys.exit(0)
+if "--wide" in sys.argv:
+    print("// GENERATED by tools/gen_tile_asm.py --wide -- do not edit.  See that script for the why.")
+    print("""// All channels of one pipeline stage for one direction PAIR, 16 sample pairs per lane (512-sample blocks).
+template <int NCH>
+__device__ __forceinline__ void tile_stage_wide(u64 (&acc)[2][16], uint32_t ent, uint32_t row, uint32_t end);
+template <int NCH>
+__device__ __forceinline__ void tile_stage_wide_exact(u64 (&acc)[2][16], uint32_t ent, uint32_t row, uint32_t end);
+""")
+    for nch in (9, 10, 11):
+        print(gen_wide(nch))
+    for nch in (9, 10):
+        print(gen_wide(nch, exact=True))
     sys.exit(0)
 
 print("// GENERATED by tools/gen_tile_asm.py -- do not edit.  See that script for the why.")
