@@ -45,12 +45,14 @@ __global__ void __launch_bounds__(kGenericThreads) das_generic_kernel(GenericArg
             const float *sig0 = base + i;
             if (a.fir) {
                 // 8-tap fractional-delay FIR of the reference's USE_FILTER build (delay.cpp:33-37):
-                // out[n] += coeffs[phase][i] * signal[n + i], i = 0..taps-1 in order, each step one fma
+                // out[n] += coeffs[phase][i] * signal[n + i], i = 0..taps-1 in order; product and sum rounded separately
+                // (that branch only exists in builds without AVX2 / FMA, delay.cpp:8 -- pinned against such a build of the
+                // reference file, oracle/_ref/libref_fir.so)
                 for (int s = 0; s < a.usable; s++) {
                     const float *sig = sig0 + s_addr[s];
                     const float *cf = a.fir + (size_t)__float_as_int(s_frac[s]) * a.fir_taps;
 #pragma unroll 8
-                    for (int t = 0; t < a.fir_taps; t++) acc = __fmaf_rn(__ldg(cf + t), __ldg(sig + t), acc);
+                    for (int t = 0; t < a.fir_taps; t++) acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + t), __ldg(sig + t)));
                 }
             } else
 #pragma unroll 8

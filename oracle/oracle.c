@@ -290,14 +290,16 @@ void orc_monopulse_gradient(const double *q, double reference, double *gradient,
 }
 
 /* ---- f4: FIR fractional-delay variant of delay() (src/dsp/delay.cpp:28-40, USE_FILTER build) ---------------- */
-/* coeffs[n_phases][taps] is filter.h's table in the reference (101 x 8); the taps accumulate in order, one fma each
- * (the reference build that would compile this is -Ofast: its contraction / order is not observable here). */
+/* coeffs[n_phases][taps] is filter.h's table in the reference (101 x 8).  The reference compiles this branch only when
+ * __AVX2__ is not defined (delay.cpp:8,28), i.e. on a host without AVX2 / FMA: oracle/_ref/libref_fir.so is that build
+ * (same file, -mno-avx2 -mno-fma) and shows what it does -- the taps accumulate in order, each product rounded and then
+ * added (no contraction).  tests/test_oracle.py pins this function to it bit for bit. */
 void orc_delay_fir(float *out, const float *signal, float fraction, int n, const float *coeffs, int n_phases, int taps) {
     float get_filter = fraction * (float)(n_phases - 1) + 0.5f;     /* fraction * 100.0f + 0.5f */
     int delay_int = (int)get_filter;
     if (delay_int > n_phases - 1) delay_int = n_phases - 1;
     for (int k = 0; k < n; k++)
-        for (int i = 0; i < taps; i++) out[k] = fmaf(coeffs[(size_t)delay_int * taps + i], signal[k + i], out[k]);
+        for (int i = 0; i < taps; i++) out[k] = out[k] + coeffs[(size_t)delay_int * taps + i] * signal[k + i];
 }
 
 void orc_mimo_update_fir(const float *window, int C, int W, int n, const int *index, int usable,

@@ -33,6 +33,7 @@ def _load(path):
 
 _lib = None
 _ref = None
+_ref_fir = None
 
 
 def lib():
@@ -53,6 +54,8 @@ def lib():
         L.orc_mimo_update_fir.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, C.c_int, _f32p,
                                           C.c_int, C.c_int, _f32p]
         L.orc_mimo_update_fir.restype = None
+        L.orc_delay_fir.argtypes = [_f32p, _f32p, C.c_float, C.c_int, _f32p, C.c_int, C.c_int]
+        L.orc_delay_fir.restype = None
         L.orc_quadrant.argtypes = [_f64p, C.c_double, C.c_double, C.c_double, _f64p, _f64p]
         L.orc_quadrant.restype = None
         L.orc_monopulse_gradient.argtypes = [_f64p, C.c_double, _f64p, _f64p]
@@ -86,6 +89,44 @@ def ref():
                                       C.c_void_p, C.c_void_p, C.c_int]
         _ref = R
     return _ref
+
+
+def ref_fir():
+    """The reference's delay.cpp compiled WITHOUT AVX2: its FIR variant of delay() (None if oracle/_ref/libref_fir.so is unavailable)."""
+    global _ref_fir
+    if _ref_fir is None:
+        path = os.path.join(_HERE, "_ref", "libref_fir.so")
+        if not os.path.exists(path):
+            if os.path.exists("/root/reference/src/dsp/delay.cpp"):
+                build()
+            if not os.path.exists(path):
+                return None
+        R = C.CDLL(path)
+        R.ref_delay.argtypes = [_f32p, _f32p, C.c_float]
+        R.ref_filter_coeffs.restype = C.POINTER(C.c_float)
+        R.ref_mimo_update.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f32p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int]
+        assert R.ref_is_fir() == 1
+        _ref_fir = R
+    return _ref_fir
+
+
+def ref_filter_table():
+    """filter_coeffs[101][8] of src/dsp/filter.h as the compiled reference object holds it."""
+    return np.ctypeslib.as_array(ref_fir().ref_filter_coeffs(), shape=(101, 8)).copy()
+
+
+def ref_mimo_update_fir(window, offsets, fractions, index=None, n=N_SAMPLES, n_threads=1):
+    """MIMOWorker::update loop around the compiled reference FIR delay() (W must cover offset + n + 7)."""
+    R = ref_fir()
+    window = np.ascontiguousarray(window, np.float32)
+    Cn, W = window.shape
+    index = _idx(index, Cn)
+    D = offsets.shape[0]
+    power = np.zeros(D, np.float32)
+    R.ref_mimo_update(window, Cn, W, n, index, len(index), np.ascontiguousarray(offsets, np.int32),
+                      np.ascontiguousarray(fractions, np.float32), D, power.ctypes.data, None, n_threads)
+    return power
 
 
 # ---- geometry / tables ------------------------------------------------------------------------

@@ -17,6 +17,16 @@ extern "C" {
 
 int ref_n_samples() { return N_SAMPLES; }
 
+// 1 when this object holds the FIR variant of delay() (built without AVX2, delay.cpp:8,28), and the reference's
+// coefficient table (src/dsp/filter.h:10-112) as that build sees it
+#if !defined(__AVX2__) && USE_FILTER
+int ref_is_fir() { return 1; }
+const float *ref_filter_coeffs() { return &filter_coeffs[0][0]; }
+#else
+int ref_is_fir() { return 0; }
+const float *ref_filter_coeffs() { return nullptr; }
+#endif
+
 void ref_delay(float *out, const float *signal, float fraction) { delay(out, signal, fraction); }
 
 // Push n_frames blocks of N_SAMPLES floats through one real Streams ring (write_stream + forward,

@@ -80,7 +80,22 @@ def main():
         cal_index=cidx, cal_corr=ccorr, cal_median=np.float32(cmed), cal_mean=np.float32(cmean),
         wire=wire, exposure=exposure)
     print("power peak", power.argmax(), "ref/oracle power max rel diff", np.max(np.abs(ref_power - power) / power))
-    for f in ("tables.npz", "snapshot.npz"):
+
+    # ---- G: the FIR variant of delay() (delay.cpp:28-40) as the reference file compiles it without AVX2 ----
+    assert O.ref_fir() is not None, "oracle/_ref/libref_fir.so missing (needs /root/reference)"
+    coeffs = O.ref_filter_table()                          # src/dsp/filter.h:10-112 as the compiled object holds it
+    fir_ref_power = O.ref_mimo_update_fir(window, off, fr)
+    fir_power = O.mimo_update_fir(window, off, fr, coeffs)
+    rng = np.random.default_rng(5)
+    sig = (0.02 * rng.standard_normal((8, 300))).astype(np.float32)
+    fracs = rng.random(8).astype(np.float32)
+    outs = np.zeros((8, 256), np.float32)
+    for k in range(8):
+        O.ref_fir().ref_delay(outs[k], sig[k], fracs[k])
+    np.savez_compressed(os.path.join(HERE, "fir.npz"), coeffs=coeffs, ref_power=fir_ref_power, power=fir_power,
+                        kat_signal=sig, kat_fraction=fracs, kat_out=outs)
+    print("FIR: oracle vs compiled reference power max rel diff", np.max(np.abs(fir_ref_power - fir_power) / fir_power))
+    for f in ("tables.npz", "snapshot.npz", "fir.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -2,8 +2,8 @@
 """Measured parity of the power maps against the CPU reference path on the BASELINE.json configurations (bar: 1e-4 max
 relative error, identical peak direction).  Kernel 2 = exact operation triple, kernel 4 = two-FMA form (automatic).
 
-Two inputs per configuration: the SURVEY 8d signal (three tones + white noise, sigma = 1e-3) and the same tones WITHOUT
-noise (sigma = 0), where the side-lobe nulls are many orders of magnitude below the peak and any re-rounding of the
+Three inputs per configuration: the SURVEY 8d signal (three tones + white noise, sigma = 1e-3), the same tones WITHOUT
+noise (sigma = 0) and a single noise-free 3 kHz tone, where the side-lobe nulls are many orders of magnitude below the peak and any re-rounding of the
 channel sum shows up in the relative error of those directions.  The CPU side is the compiled reference delay() loop
 (oracle/_ref, all host threads) when it is available, else the C restatement (bit-identical delayed sums, see
 tests/test_oracle.py); every direction of every grid is compared (cfg5: all 65 536).
@@ -34,8 +34,9 @@ def main():
         org = cases.origins(c["nx"], c["ny"])
         w = bflk.MIMOWorker(org, c["rows"], c["cols"], c["fov"], frame_len=c["N"], history=c["H"], window_len=c["W"])
         off, fr = w.tables()
-        for sigma in (1e-3, 0.0):
-            window = synth.make_stream(synth.tile_geometry(org), c["W"], sigma=sigma)
+        one_tone = ((np.deg2rad(20.0), np.deg2rad(30.0), 3000.0, 1e-2),)
+        for sigma, sources, label in ((1e-3, synth.DEFAULT_SOURCES, "3 tones"), (0.0, synth.DEFAULT_SOURCES, "3 tones"), (0.0, one_tone, "1 tone")):
+            window = synth.make_stream(synth.tile_geometry(org), c["W"], sources=sources, sigma=sigma)
             po, who = cpu_power(window, off, fr, c["N"])
             po = po.astype(np.float64)
             for k in (2, 4):
@@ -44,8 +45,8 @@ def main():
                 err = np.abs(p - po) / po
                 worst = int(np.argmax(err))
                 rel_to_peak = np.abs(p - po).max() / po.max()
-                print(f"{name} sigma {sigma:g} kernel {k}: max rel err {err.max():.2e} (direction {worst}, power {po[worst] / po.max():.1e} of the peak), "
-                      f"median {np.median(err):.1e}, max |diff| / peak {rel_to_peak:.1e}, {len(po)} directions, "
+                print(f"{name} {label} sigma {sigma:g} kernel {k}: max rel err {err.max():.2e} (direction {worst}, power {po[worst] / po.max():.1e} of the peak), "
+                      f"median {np.median(err):.1e}, weakest direction {po.min() / po.max():.1e} of the peak, max |diff| / peak {rel_to_peak:.1e}, {len(po)} directions, "
                       f"peak direction {'identical' if int(np.argmax(p)) == int(np.argmax(po)) else 'DIFFERS'} ({int(np.argmax(po))}); CPU: {who}")
                 sys.stdout.flush()
 
