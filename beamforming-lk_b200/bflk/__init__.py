@@ -33,6 +33,11 @@ SYMBOLS = [
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
+    "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
+    "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded",
+    "bflk_group_create", "bflk_group_destroy", "bflk_group_size", "bflk_group_handle", "bflk_group_last_error",
+    "bflk_group_set_geometry", "bflk_group_set_tiled_geometry", "bflk_group_set_channel_mask", "bflk_group_set_grid_fov",
+    "bflk_group_set_kernel", "bflk_group_power_map_batch", "bflk_group_power_map_batch_dev", "bflk_group_synchronize",
 ]
 
 
@@ -96,6 +101,28 @@ def load_library():
     L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
     L.bflk_calibrate.argtypes = [vp, vp, i32, f32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
     L.bflk_ingest_i32.argtypes = [vp, vp, i32, i32, vp]
+    L.bflk_comm_unique_id.argtypes = [vp]
+    L.bflk_comm_init_rank.argtypes = [vp, vp, i32, i32, i32]
+    L.bflk_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.bflk_shard_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.bflk_power_map_batch_sharded_dev.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_power_map_batch_sharded.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_group_create.argtypes = [C.POINTER(Config), vp, i32, i32, C.POINTER(vp)]
+    L.bflk_group_destroy.argtypes = [vp]
+    L.bflk_group_size.argtypes = [vp]
+    L.bflk_group_size.restype = i32
+    L.bflk_group_handle.argtypes = [vp, i32]
+    L.bflk_group_handle.restype = vp
+    L.bflk_group_last_error.argtypes = [vp]
+    L.bflk_group_last_error.restype = C.c_char_p
+    L.bflk_group_set_geometry.argtypes = [vp, vp, i32]
+    L.bflk_group_set_tiled_geometry.argtypes = [vp, i32, vp]
+    L.bflk_group_set_channel_mask.argtypes = [vp, vp, i32]
+    L.bflk_group_set_grid_fov.argtypes = [vp, i32, i32, f32]
+    L.bflk_group_set_kernel.argtypes = [vp, i32]
+    L.bflk_group_power_map_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_group_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_group_synchronize.argtypes = [vp]
     _lib = L
     return L
 
@@ -106,6 +133,26 @@ def _np(a, dtype):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def shard_plan(n_directions, n_frames, n_ranks, rank, dir_groups=0):
+    """(dir_first, dir_count, frame_first, frame_count) of rank `rank` (bflk_shard_plan; needs no device)."""
+    L = load_library()
+    a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = L.bflk_shard_plan(n_directions, n_frames, n_ranks, dir_groups, rank, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    if rc != 0:
+        raise BflkError(rc, f"bflk_shard_plan({n_directions}, {n_frames}, {n_ranks}, {dir_groups}, {rank})")
+    return a.value, b.value, c.value, d.value
+
+
+def comm_unique_id():
+    """128 bytes identifying a new multi-GPU job (rank 0 creates it, the caller broadcasts it)."""
+    L = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = L.bflk_comm_unique_id(buf)
+    if rc != 0:
+        raise BflkError(rc, "bflk_comm_unique_id: NCCL is not available")
+    return bytes(buf)
 
 
 def tile_origins(nx, ny, pitch=0.16):
@@ -156,6 +203,25 @@ class Beamformer:
 
     def launch_count(self):
         return int(self._L.bflk_launch_count(self._h))
+
+    # -- multi-GPU: this handle as one rank of a job (one process per GPU) ---------------------------------------
+    def comm_init_rank(self, unique_id, n_ranks, rank, dir_groups=0):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._L.bflk_comm_init_rank(self._h, buf, n_ranks, rank, dir_groups))
+
+    def comm_info(self):
+        """(n_ranks, rank, direction groups, frame groups, collectives issued so far)."""
+        a, b, c, d, e = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self._L.bflk_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        return a.value, b.value, c.value, d.value, e.value
+
+    def power_map_batch_sharded_dev(self, stream_dev_ptr, n_samples, n_frames, power_all_dev_ptr, cuda_stream=0):
+        self._check(self._L.bflk_power_map_batch_sharded_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
+                                                             C.c_void_p(power_all_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_sharded_ptr(self, stream_ptr, n_samples, n_frames, power_ptr):
+        self._check(self._L.bflk_power_map_batch_sharded(self._h, C.c_void_p(stream_ptr), n_samples, n_frames,
+                                                         C.c_void_p(power_ptr) if power_ptr else None))
 
     def kernel_info(self):
         """(last kernel used: 1 generic / 2 tiled, tile span, window chunks of the tiled variant)."""
@@ -370,3 +436,56 @@ class MISOWorker(Beamformer):
     def update(self, window):
         """beamformer.steer(direction); beamformer.das(data) (src/dsp/miso.cpp:42-46) for every target."""
         return self.miso(self.theta, self.phi, window)
+
+
+class Group:
+    """One process, several GPUs (bflk_group_*): the grid (x the frames of a batch) sharded across `devices`."""
+
+    def __init__(self, origins, rows, columns, fov, devices, dir_groups=0, frame_len=N_SAMPLES, history=N_SAMPLES,
+                 window_len=WINDOW, kernel=0):
+        self._L = load_library()
+        origins = np.asarray(origins, np.float32).reshape(-1, 3)
+        cfg = Config()
+        self._L.bflk_default_config(C.byref(cfg))
+        cfg.n_channels, cfg.frame_len, cfg.history, cfg.window_len = ELEMENTS * origins.shape[0], frame_len, history, window_len
+        self.cfg = cfg
+        devs = np.asarray(devices, np.int32)
+        self._g = C.c_void_p()
+        rc = self._L.bflk_group_create(C.byref(cfg), _ptr(devs), devs.shape[0], dir_groups, C.byref(self._g))
+        if rc != 0:
+            raise BflkError(rc, self._L.bflk_last_error(None).decode() or "bflk_group_create failed (NCCL missing?)")
+        self.n_dir = rows * columns
+        self._check(self._L.bflk_group_set_tiled_geometry(self._g, origins.shape[0], _ptr(origins)))
+        self._check(self._L.bflk_group_set_grid_fov(self._g, rows, columns, float(fov)))
+        self._check(self._L.bflk_group_set_kernel(self._g, kernel))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BflkError(rc, self._L.bflk_group_last_error(self._g).decode())
+
+    def size(self):
+        return int(self._L.bflk_group_size(self._g))
+
+    def power_map_batch(self, stream, n_frames):
+        stream = _np(stream, np.float32)
+        out = np.zeros((n_frames, self.n_dir), np.float32)
+        self._check(self._L.bflk_group_power_map_batch(self._g, _ptr(stream), stream.shape[1], n_frames, _ptr(out)))
+        return out
+
+    def power_map_batch_dev(self, stream_ptrs, n_samples, n_frames, power_ptrs):
+        n = self.size()
+        a = (C.c_void_p * n)(*stream_ptrs)
+        b = (C.c_void_p * n)(*power_ptrs)
+        self._check(self._L.bflk_group_power_map_batch_dev(self._g, a, n_samples, n_frames, b))
+        self._check(self._L.bflk_group_synchronize(self._g))
+
+    def close(self):
+        if getattr(self, "_g", None) is not None and self._g.value:
+            self._L.bflk_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -63,6 +63,14 @@ int bflk_create(const bflk_config *cfg, bflk_handle **out) {
     bflk_handle *h = new bflk_handle();
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
+    // tuning knobs: read once here, never on a call path (a worker thread calls bflk_power_map every 5 ms)
+    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    h->tuning.tile_nch = env_int("BFLK_TILE_NCH", 0);
+    h->tuning.tile_warps = env_int("BFLK_TILE_WARPS", 0);
+    h->tuning.tile_stages = env_int("BFLK_TILE_STAGES", 0);
+    h->tuning.tile_pairs = env_int("BFLK_TILE_PAIRS", 0);
+    h->tuning.tile_mode = env_int("BFLK_TILE_MODE", -1);
+    h->tuning.chunk_mib = env_int("BFLK_CHUNK_MIB", 0);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
         return create_fail(BFLK_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -74,6 +82,7 @@ int bflk_create(const bflk_config *cfg, bflk_handle **out) {
 int bflk_destroy(bflk_handle *h) {
     if (!h) return BFLK_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
+    comm_release(h);
     if (h->stream) {
         cudaStreamSynchronize(h->stream);
         cudaStreamDestroy(h->stream);
@@ -405,17 +414,25 @@ int bflk_kernel_time_ms(bflk_handle *h, float *das_ms, int32_t *das_launches, fl
     return BFLK_OK;
 }
 
-static int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
+}  // extern "C"
+
+namespace bflk {
+
+int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
     return (int64_t)(n_frames - 1) * h->cfg.frame_len + h->cfg.history + h->cfg.frame_len + 1;
 }
 
-// Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.
-static int ensure_tiles(bflk_handle *h, int fast) {
+// Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.  tiles_valid is set only after
+// the last step has succeeded, so a failed build is retried (and reported again) by the next call.
+int ensure_tiles(bflk_handle *h, int fast) {
     if (h->tiles_valid && h->tiles_fast == fast) return BFLK_OK;
-    h->tiles_valid = true;
+    h->tiles_valid = false;
     h->tiles_fast = fast;
     h->tiles_usable = false;
-    if (h->rows <= 0 || h->cols <= 0) return BFLK_OK;  // caller-supplied LUT: no grid structure to tile
+    if (h->rows <= 0 || h->cols <= 0) {  // caller-supplied LUT without a declared grid shape: nothing to tile
+        h->tiles_valid = true;
+        return BFLK_OK;
+    }
     const int cols = h->cols;
     const int row0 = (h->dir_first / cols) & ~1;
     const int row1 = (h->dir_first + h->dir_count - 1) / cols;  // inclusive
@@ -439,33 +456,26 @@ static int ensure_tiles(bflk_handle *h, int fast) {
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     const int span0 = h->p_misc.p[0], span1 = h->p_misc.p[1], span2 = h->p_misc.p[2];
     // one shared window while the 2x2 spread fits the 6- or 8-chunk variant; beyond that (coarse grid, long array) the
-    // direction pairs along the array's short axis still fit a 6- / 7-chunk window each: measured faster than the
-    // 10-chunk single window (fewer dispatch cases, smaller code, more resident warps)
+    // direction pairs along the array's short axis still fit a 6- / 7-chunk window each: measured faster than one wide
+    // window (fewer dispatch cases, smaller code, more resident warps; two-FMA form: cfg2 0.576 vs 0.568, cfg3 0.539 vs
+    // 0.455 of the FP32 peak)
     int mode = 0;
     const int pair_span = std::min(span1, span2), pair_mode = span1 <= span2 ? 1 : 2;
     if (span0 > 3 && pair_span <= 3) mode = pair_mode;        // two 6-chunk windows, 16 warps
     else if (span0 > 7 && pair_span <= 5) mode = pair_mode;   // two 7-chunk windows instead of one 10-chunk window
-    if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
-        const int v = atoi(env);
-        if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
-    }
-    if (fast) {
-        // the two-FMA variant keeps no differences, so one window of up to 10 chunks fits its registers; two 6-chunk
-        // windows (2-bit dispatch trees, small code, the second one skipped where the tile fits the first) are still
-        // faster as soon as the 2x2 spread needs more than 6 chunks (measured: cfg2 0.576 vs 0.568, cfg3 0.539 vs 0.455)
-        mode = 0;
-        if (span0 > 3 && pair_span <= 3) mode = pair_mode;
-        else if (span0 > 7 && pair_span <= 5) mode = pair_mode;
-        if (const char *env = getenv("BFLK_TILE_MODE")) {  // tuning knob
-            const int v = atoi(env);
-            if (v == 0 || ((v == 1 || v == 2) && h->p_misc.p[v] <= 5)) mode = v;
-        }
-    }
+    const int forced = h->tuning.tile_mode;
+    if (forced == 0 || ((forced == 1 || forced == 2) && h->p_misc.p[forced] <= 5)) mode = forced;
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[mode];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast);
-    h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0;
-    if (!h->tiles_usable) return BFLK_OK;
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast, &h->tuning);
+    // usable: the spread fits a compiled variant, frames are whole blocks, AND the stage ring of some CTA shape fits
+    // shared memory (packed rows grow with the largest delay: long arrays fall through to the other kernels)
+    h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0 &&
+                      h->tile_geom.stages >= 3;
+    if (!h->tiles_usable) {
+        h->tiles_valid = true;
+        return BFLK_OK;
+    }
     // pass 2: the packed per-(tile, channel) entries, grouped for that variant's CTA shape
     const size_t entries = tile_table_entries(n_tiles, usable, h->tile_geom.warps);
     const size_t ent_bytes = das_tile_entry_bytes(h->tile_geom);
@@ -477,8 +487,13 @@ static int ensure_tiles(bflk_handle *h, int fast) {
                                     h->d_tile_dirs.p, n_tiles, h->d_misc.p, h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->tiles_valid = true;
     return BFLK_OK;
 }
+
+}  // namespace bflk
+
+extern "C" {
 
 // Builds (once per grid / mask / range) the direction tiles and per-lane tables of the lane-broadcast kernel.
 static int ensure_bcast(bflk_handle *h) {
@@ -533,8 +548,10 @@ static int ensure_bcast(bflk_handle *h) {
 }
 
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold row_len valid samples
-static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
-                         float *power_dev, void *cuda_stream) {
+}  // extern "C"
+
+int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
+                        float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
     if (!stream_dev || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
@@ -558,12 +575,12 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
         if (rc) return rc;
         tiled = h->tiles_usable && !(row_stride & 1) && !((uintptr_t)stream_dev & 7);  // packed rows: 8-byte loads
         if (h->kernel_choice != 0 && !tiled)
-            return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (span %d > %d)",
-                           h->tile_smax, das_tile_max_span());
+            return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (offset spread %d of at most %d, %d stage buffers fit shared memory)",
+                           h->tile_smax, das_tile_max_span(), h->tile_geom.stages);
     }
-    const bool bcast_ok = N >= 256;
+    const bool bcast_ok = N >= 256 && das_bcast_fits(das_bcast_geometry(h->cfg.history, h->max_delay));
     if (h->kernel_choice == 3 && !bcast_ok)
-        return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256");
+        return h->fail(BFLK_ERR_STATE, "bflk_power_map: the lane-broadcast kernel needs frame_len >= 256 and a stage ring that fits shared memory");
     if (!fir && !tiled && (h->kernel_choice == 0 || h->kernel_choice == 3) && bcast_ok) {
         int rc = ensure_bcast(h);
         if (rc) return rc;
@@ -650,30 +667,29 @@ static int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_st
     return BFLK_OK;
 }
 
+extern "C" {
+
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream) {
     return power_map_dev(h, stream_dev, n_samples, n_samples, n_frames, power_dev, cuda_stream);
 }
 
-int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
-    if (!h) return BFLK_ERR_INVALID;
-    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
-    if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
-    if (n_samples < min_stream_samples(h, n_frames))
-        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
-                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
-    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+}  // extern "C"
+
+namespace bflk {
+
+// samples a frame needs beyond its own N (the FIR interpolation reads taps - 2 more)
+int64_t frame_tail_samples(const bflk_handle *h) {
+    return min_stream_samples(h, 1) - h->cfg.frame_len + (h->fir_phases > 0 ? h->fir_taps - 2 : 0);
+}
+
+// Host batches go up in chunks of frames: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k.
+// A chunk is ~32 MiB of new samples (measured on B200 / PCIe 5 at cfg3 with wave-aligned chunks: 32 MiB 64.7 k maps/s,
+// 64 MiB 61.6 k, 96 MiB 56.9 k), rounded to whole CTA waves of the tiled kernel so PCIe and the SMs both stay busy;
+// small batches are one chunk.
+int host_chunk_frames(bflk_handle *h, int n_frames, int *chunk_frames_out) {
     const int C = h->cfg.n_channels, N = h->cfg.frame_len;
-    const size_t n_in = (size_t)C * n_samples, n_out = (size_t)n_frames * h->dir_count;
-    BFLK_CUDA(h, h->d_window.reserve(n_in));
-    BFLK_CUDA(h, h->d_power.reserve(n_out));
-    // Chunks of frames: the H2D copy of chunk k+1 (copy_stream) overlaps the kernels of chunk k (stream).
-    // A chunk is ~32 MiB of new samples, rounded to whole CTA waves, so PCIe and the SMs both stay busy; small batches
-    // are one chunk.
-    // samples a frame needs beyond its own N (the FIR interpolation reads taps - 2 more)
-    const int64_t tail = min_stream_samples(h, 1) - N + (h->fir_phases > 0 ? h->fir_taps - 2 : 0);
-    int64_t chunk_bytes = 32ll << 20;  // measured on B200 / PCIe 5 at cfg3 with wave-aligned chunks: 32 MiB 64.7 k maps/s, 64 MiB 61.6 k, 96 MiB 56.9 k
-    if (const char *env = getenv("BFLK_CHUNK_MIB")) chunk_bytes = std::max(1, atoi(env)) * (1ll << 20);  // tuning knob
+    const int64_t chunk_bytes = (int64_t)(h->tuning.chunk_mib > 0 ? h->tuning.chunk_mib : 32) << 20;
     const int64_t frame_bytes = (int64_t)C * N * sizeof(float);
     int n_chunks = (int)std::max<int64_t>(1, ((int64_t)n_frames * frame_bytes + chunk_bytes / 2) / chunk_bytes);
     int chunk_frames = (n_frames + n_chunks - 1) / n_chunks;  // even split
@@ -690,7 +706,32 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
             if (k * quantum < n_frames) chunk_frames = k * quantum;
         }
     }
-    n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    chunk_frames += chunk_frames & 1;                                 // block pairs
+    *chunk_frames_out = std::max(2, chunk_frames);
+    return BFLK_OK;
+}
+
+}  // namespace bflk
+
+extern "C" {
+
+int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
+    if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    if (n_samples < min_stream_samples(h, n_frames))
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
+                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int C = h->cfg.n_channels, N = h->cfg.frame_len;
+    const size_t n_in = (size_t)C * n_samples, n_out = (size_t)n_frames * h->dir_count;
+    BFLK_CUDA(h, h->d_window.reserve(n_in));
+    BFLK_CUDA(h, h->d_power.reserve(n_out));
+    const int64_t tail = frame_tail_samples(h);
+    int chunk_frames = n_frames;
+    int rc = host_chunk_frames(h, n_frames, &chunk_frames);
+    if (rc) return rc;
+    const int n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
     if (!h->copy_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     while ((int)h->chunk_events.size() < n_chunks) {
         cudaEvent_t e;
@@ -710,7 +751,7 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
         BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
         BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
         float *pk = h->d_power.p + (size_t)f0 * h->dir_count;
-        int rc = power_map_dev(h, h->d_window.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        rc = power_map_dev(h, h->d_window.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
         if (rc) return rc;
         BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
                                      cudaMemcpyDeviceToHost, h->stream));

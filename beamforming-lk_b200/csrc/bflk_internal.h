@@ -63,6 +63,16 @@ inline size_t tile_table_entries(int n_tiles, int usable, int warps) {
     return groups * stages * warps * kTileCC;
 }
 
+// Tuning knobs (BFLK_* environment variables), read ONCE in bflk_create -- never on a call path.  0 / -1 = not set.
+struct Tuning {
+    int tile_nch = 0;        // BFLK_TILE_NCH: window chunks of the two-FMA variant (>= what the grid needs)
+    int tile_warps = 0;      // BFLK_TILE_WARPS: 10, 11, 12 or 16 compute warps per CTA
+    int tile_stages = 0;     // BFLK_TILE_STAGES: 3 or 4 stage buffers
+    int tile_pairs = 0;      // BFLK_TILE_PAIRS: block pairs per CTA
+    int tile_mode = -1;      // BFLK_TILE_MODE: 0 one window per 2x2 tile, 1 / 2 one window per direction pair
+    int chunk_mib = 0;       // BFLK_CHUNK_MIB: host batches are uploaded in chunks of about this size
+};
+
 // Shape of the packed rows the tiled kernel stages (das_tile.cu).
 struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
@@ -73,6 +83,8 @@ struct TileGeometry {
     int row_chunks = 0;  // logical chunks per packed row
     int copy_bytes = 0;  // padded bytes of one copy of a packed row
     int row_bytes = 0;   // bytes per packed row: the even-aligned copy followed by the copy shifted by one sample pair
+    int stages = 0;      // stage buffers that fit shared memory (4 or 3; 0 = the variant does not fit at all)
+    int pairs_per_cta = 0;  // 0 = automatic
 };
 
 // ---- lane-broadcast kernel (das_bcast.cu) -----------------------------------------------------------------
@@ -130,8 +142,12 @@ struct PinBuf {
 
 }  // namespace bflk
 
+struct bflk_comm;   // multi.cu: NCCL communicator state of a handle that is one rank of a multi-GPU job
+
 struct bflk_handle {
     bflk_config cfg{};
+    bflk::Tuning tuning;
+    bflk_comm *comm = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     std::string error;
@@ -275,7 +291,10 @@ typedef void (*TileLaunchHook)(void *ctx, int kind, bool begin, cudaStream_t st)
 cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, int *launches, TileLaunchHook hook = nullptr,
                             void *hook_ctx = nullptr);
 int das_tile_max_span();
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0, int fast = 0);
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0, int fast = 0,
+                               const Tuning *tuning = nullptr);
+// shared memory the variant needs with `stages` stage buffers
+size_t das_tile_smem_bytes(const TileGeometry &g, int stages);
 size_t das_tile_packed_bytes(const TileArgs &a);
 size_t das_tile_entry_bytes(const TileGeometry &g);
 
@@ -294,6 +313,7 @@ struct BcastArgs {
     float norm;
 };
 BcastGeometry das_bcast_geometry(int history, int max_delay);
+bool das_bcast_fits(const BcastGeometry &g);
 size_t das_bcast_table_entries(int n_tiles, int usable);
 size_t das_bcast_packed_bytes(const BcastArgs &a);
 cudaError_t launch_bcast_table(const int32_t *d_off, const float *d_frac, int C, const int32_t *d_index, int usable,
@@ -306,5 +326,17 @@ cudaError_t launch_das_bcast(const BcastArgs &a, cudaStream_t st, int *launches,
 cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st);
 cudaError_t launch_channel_power(const float *d_signals, int n_ch, int W, float *d_power, cudaStream_t st);
 cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *d_exposure, cudaStream_t st);
+
+// ---- bflk_api.cu internals used by multi.cu ---------------------------------------------------------------
+// stream_dev: first sample of frame 0; rows are row_stride floats apart and hold n_samples valid samples
+int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
+                  float *power_dev, void *cuda_stream);
+int ensure_tiles(bflk_handle *h, int fast);
+int64_t min_stream_samples(const bflk_handle *h, int n_frames);
+// frames per chunk of a host batch of n_frames (whole CTA waves of the tiled kernel where it applies) and the samples a
+// frame needs beyond its own N
+int host_chunk_frames(bflk_handle *h, int n_frames, int *chunk_frames);
+int64_t frame_tail_samples(const bflk_handle *h);
+void comm_release(bflk_handle *h);   // multi.cu
 
 }  // namespace bflk

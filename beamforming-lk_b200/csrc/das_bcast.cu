@@ -238,13 +238,23 @@ cudaError_t launch_bcast_table(const int32_t *d_off, const float *d_frac, int C,
     return cudaGetLastError();
 }
 
+static size_t bcast_smem_bytes(const BcastGeometry &g) {
+    return (size_t)kStages * (kCC * g.row_bytes + kCC * 32 * sizeof(BcastEntry)) + 2 * kStages * 8;
+}
+
+// packed rows grow with the largest delay: beyond ~330 samples of history the stage ring no longer fits shared memory
+bool das_bcast_fits(const BcastGeometry &g) {
+    const size_t smem = bcast_smem_bytes(g);
+    return smem <= 227 * 1024 && smem >= (size_t)kWarps * 32 * 24;
+}
+
 cudaError_t launch_das_bcast(const BcastArgs &a, cudaStream_t st, int *launches, TileLaunchHook hook, void *hook_ctx) {
     const int nblk = blocks_per_frame(a.frame_len);
     const int n_items = a.n_frames * nblk;
     const int n_pairs = (n_items + 1) / 2;
     if (a.frame_len < kBlock) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)kStages * (kCC * a.geom.row_bytes + kCC * 32 * sizeof(BcastEntry)) + 2 * kStages * 8;
-    if (smem > 227 * 1024 || smem < (size_t)kWarps * 32 * 24) return cudaErrorInvalidConfiguration;
+    const size_t smem = bcast_smem_bytes(a.geom);
+    if (!das_bcast_fits(a.geom)) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(bcast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
 

@@ -280,7 +280,14 @@ __global__ void finalize_kernel(const float *__restrict__ partial, int n_frames,
 // ---- host side ---------------------------------------------------------------------------------------------------
 int das_tile_max_span() { return 11; }
 
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast) {
+size_t das_tile_entry_bytes(const TileGeometry &g);
+
+size_t das_tile_smem_bytes(const TileGeometry &g, int stages) {
+    // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
+    return (size_t)stages * (kCC * g.row_bytes + g.warps * kCC * das_tile_entry_bytes(g)) + stages * (8 + 4) + 96;
+}
+
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast, const Tuning *tuning) {
     TileGeometry g;
     g.mode = mode;
     g.fast = fast;
@@ -289,31 +296,44 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     g.nch = max_span <= 1 && mode == 0 ? 5 : (max_span <= 3 ? 6 : (max_span <= 5 ? 7 : (max_span <= 7 ? 8 : 10)));
     if (fast) {
         g.nch = std::max(mode ? 6 : 5, (9 + max_span + 1) / 2);
-        if (const char *env = getenv("BFLK_TILE_NCH")) g.nch = std::min(mode ? 7 : 10, std::max(g.nch, atoi(env)));  // tuning knob
+        if (tuning && tuning->tile_nch > 0) g.nch = std::min(mode ? 7 : 10, std::max(g.nch, tuning->tile_nch));
     }
     // Warps (= direction tiles) per CTA.  The kernel is issue-bound (an FFMA2 / FADD2 holds a scheduler's issue
     // port for two cycles), so more resident warps help only while registers allow: the 6-chunk variant fits
     // 128 registers (16 warps, +5 % over 12); the 8- and 10-chunk variants need ~150-165 (12 warps; 16 would
     // spill).  Smaller CTAs only when a small direction shard (multi-GPU) would leave the last CTA mostly idle.
+    const bool can16 = g.nch <= 6 || (fast && g.nch <= kFastMaxNch16 && !(mode != 0 && g.nch > 7));
+    const bool exact_dual7 = !fast && mode != 0 && g.nch == 7;   // compiled for 10 - 12 warps only
     const int n_cand = 4;
     const int cand[n_cand] = {16, 12, 11, 10};
-    const double tlp[n_cand] = {g.nch <= 6 || (fast && g.nch <= kFastMaxNch16) ? 1.05 : 0.0, 1.0, 0.95, 0.88};
-    g.warps = 12;
-    double best = 0.0;
-    for (int i = 0; i < n_cand; i++) {
-        const int tiles = n_tiles > 0 ? n_tiles : 1 << 20;
-        const int groups = (tiles + cand[i] - 1) / cand[i];
-        const double score = tlp[i] * tiles / (double)(groups * cand[i]);
-        if (score > best + 1e-9) { best = score; g.warps = cand[i]; }
-    }
-    if (const char *env = getenv("BFLK_TILE_WARPS")) {  // tuning knob
-        const int v = atoi(env);
-        if ((v >= 10 && v <= 12) || v == 16) g.warps = v;
-    }
-    // largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
+    const double tlp[n_cand] = {can16 && !exact_dual7 ? 1.05 : 0.0, 1.0, 0.95, 0.88};
+    int forced = 0;
+    if (tuning && ((tuning->tile_warps >= 10 && tuning->tile_warps <= 12) || (tuning->tile_warps == 16 && !exact_dual7)))
+        forced = tuning->tile_warps;
+    // the largest logical chunk a lane can touch: (H - stage_off)/2 + 4*31 + nch - 1
     g.row_chunks = (history - g.stage_off) / 2 + 4 * 31 + g.nch;
     g.copy_bytes = 16 * (padded_chunk(g.row_chunks - 1) + 1);
     g.row_bytes = 2 * g.copy_bytes;  // even-aligned copy + copy shifted by one sample pair
+    // pick the best-scoring CTA shape whose stage ring fits shared memory (long arrays: packed rows grow with the largest
+    // delay); 4 stage buffers where they fit, else 3; stages == 0 tells the caller that no shape fits
+    double best = 0.0;
+    g.warps = 0;
+    g.stages = 0;
+    for (int i = 0; i < n_cand; i++) {
+        if (forced && cand[i] != forced) continue;
+        if (tlp[i] <= 0.0 && !forced) continue;
+        TileGeometry t = g;
+        t.warps = cand[i];
+        int stages = tuning && tuning->tile_stages == 3 ? 3 : kMaxStages;
+        if (das_tile_smem_bytes(t, stages) > 227 * 1024) stages = 3;
+        if (das_tile_smem_bytes(t, stages) > 227 * 1024) continue;
+        const int tiles = n_tiles > 0 ? n_tiles : 1 << 20;
+        const int groups = (tiles + cand[i] - 1) / cand[i];
+        const double score = (forced ? 1.0 : tlp[i]) * tiles / (double)(groups * cand[i]);
+        if (score > best + 1e-9) { best = score; g.warps = cand[i]; g.stages = stages; }
+    }
+    if (g.warps == 0) g.warps = 12;   // nothing fits: stages stays 0
+    g.pairs_per_cta = tuning && tuning->tile_pairs > 0 ? tuning->tile_pairs : 0;
     return g;
 }
 
@@ -359,14 +379,9 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.copy_bytes = a.geom.copy_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
     const int kWarps = a.geom.warps;
-    const size_t ent_bytes = das_tile_entry_bytes(a.geom);
-    // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
-    int stages = kMaxStages;
-    auto smem_for = [&](int n) { return (size_t)n * (kCC * a.geom.row_bytes + kWarps * kCC * ent_bytes) + n * (8 + 4) + 96; };
-    if (const char *env = getenv("BFLK_TILE_STAGES")) stages = atoi(env) == 3 ? 3 : 4;  // tuning knob
-    if (smem_for(stages) > 227 * 1024) stages = 3;
-    const size_t smem = smem_for(stages);
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    const int stages = a.geom.stages;
+    if (stages < 3) return cudaErrorInvalidConfiguration;   // ensure_tiles never selects such a geometry
+    const size_t smem = das_tile_smem_bytes(a.geom, stages);
 
     KernelArgs k{};
     k.packed = reinterpret_cast<const char *>(a.packed);
@@ -399,8 +414,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (e != cudaSuccess) return e;
         ks.n_pairs = np;
         // a CTA lives ~0.6 us per channel: with few channels several block pairs per CTA hide its ramp-up and epilogue
-        ks.pairs_per_cta = std::max(1, std::min(8, 512 / std::max(1, a.usable)));
-        if (const char *env = getenv("BFLK_TILE_PAIRS")) ks.pairs_per_cta = std::max(1, atoi(env));  // tuning knob
+        ks.pairs_per_cta = a.geom.pairs_per_cta > 0 ? a.geom.pairs_per_cta : std::max(1, std::min(8, 512 / std::max(1, a.usable)));
         dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta);
         if (hook) hook(hook_ctx, 0, true, st);
         if (a.geom.fast && a.geom.mode != 0) {

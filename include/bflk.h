@@ -23,6 +23,9 @@
  *   bflk_heatmap                    MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95)
  *   bflk_calibrate                  AWProcessingUnit::calibrate mask (aw_processing_unit.cpp:126-200)
  *   bflk_ingest_i32, bflk_power_map_i32   Pipeline::receive_exposure conversion (src/fpga/pipeline.cpp:260-297)
+ *   bflk_comm_*, bflk_shard_plan, bflk_power_map_batch_sharded*, bflk_group_*   (no reference counterpart: the reference
+ *                                   is single-threaded per worker, src/dsp/worker.h:90; AWProcessingUnit::start,
+ *                                   src/aw_processing_unit/aw_processing_unit.cpp:67-95, is where a group is created)
  */
 #ifndef BFLK_H
 #define BFLK_H
@@ -122,6 +125,52 @@ int64_t bflk_launch_count(const bflk_handle *h);
  * counts since the last call, and resets the accumulators. */
 int bflk_enable_timing(bflk_handle *h, int32_t on);
 int bflk_kernel_time_ms(bflk_handle *h, float *das_ms, int32_t *das_launches, float *pack_ms, int32_t *pack_launches);
+
+/* ---- multi-GPU: the grid (x the frames of a batch) sharded across the GPUs of one box ---------------- */
+/* Every direction's power is independent (src/dsp/mimo.cpp:121-151), so G ranks are arranged as G_d direction groups x
+ * G_f frame groups (G = G_d * G_f): rank r computes direction slice r % G_d of the row-major grid for frame slice
+ * r / G_d of a batch, and ONE NCCL all-gather per batch assembles the complete [B][D] maps on every rank.  Channels
+ * are never sharded (that would reorder the channel sum).  dir_groups: G_d; 0 = automatic (2 when G is even, else 1);
+ * dir_groups = G is the pure grid sharding, dir_groups = 1 the pure batch sharding.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls fail and the single-GPU API is unaffected.
+ *
+ * (a) one process per GPU: rank 0 calls bflk_comm_unique_id, the caller broadcasts the 128 bytes, every rank calls
+ *     bflk_comm_init_rank on its own handle (collective).  All ranks then set the same geometry / grid / mask and call
+ *     the sharded entry points together. */
+int bflk_comm_unique_id(uint8_t *id128);
+int bflk_comm_init_rank(bflk_handle *h, const uint8_t *id128, int32_t n_ranks, int32_t rank, int32_t dir_groups);
+int bflk_comm_info(const bflk_handle *h, int32_t *n_ranks, int32_t *rank, int32_t *dir_groups, int32_t *frame_groups,
+                   int64_t *collectives);
+/* The slice rank `rank` of `n_ranks` computes (pure arithmetic, needs no device). */
+int bflk_shard_plan(int32_t n_directions, int32_t n_frames, int32_t n_ranks, int32_t dir_groups, int32_t rank,
+                    int32_t *dir_first, int32_t *dir_count, int32_t *frame_first, int32_t *frame_count);
+/* stream_dev[C][n_samples]: the SAME batch resident on every rank's device; power_all_dev[B][D] complete on every rank.
+ * Asynchronous on cuda_stream (NULL = the handle's stream). */
+int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                                     float *power_all_dev, void *cuda_stream);
+/* Host buffers: every rank passes the same batch stream[C][n_samples] (pinned memory recommended) but reads only the
+ * C / G_d channel rows of its own frame slice; the slice is replicated inside its frame group over NVLink, chunk by
+ * chunk, overlapping the kernels.  power_out[B][D] (NULL on ranks that do not need the maps).  Synchronous. */
+int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* (b) one process, several devices (single-process callers such as the reference's AWProcessingUnit): n_devices
+ *     handles, one per device_ids[i], sharing one job; the setters apply to every member. */
+typedef struct bflk_group bflk_group;
+int bflk_group_create(const bflk_config *cfg, const int32_t *device_ids, int32_t n_devices, int32_t dir_groups, bflk_group **out);
+int bflk_group_destroy(bflk_group *g);
+int32_t bflk_group_size(const bflk_group *g);
+bflk_handle *bflk_group_handle(bflk_group *g, int32_t i);
+const char *bflk_group_last_error(const bflk_group *g);
+int bflk_group_set_geometry(bflk_group *g, const float *xyz, int32_t n_channels);
+int bflk_group_set_tiled_geometry(bflk_group *g, int32_t n_tiles, const float *origins);
+int bflk_group_set_channel_mask(bflk_group *g, const int32_t *index, int32_t usable);
+int bflk_group_set_grid_fov(bflk_group *g, int32_t rows, int32_t cols, float fov_deg);
+int bflk_group_set_kernel(bflk_group *g, int32_t which);
+/* stream[C][n_samples] on the host -> power_out[B][D] on the host; all devices of the group work on it. */
+int bflk_group_power_map_batch(bflk_group *g, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* stream_dev[i] / power_all_dev[i]: the batch and the [B][D] result on device i.  Asynchronous on each member's stream. */
+int bflk_group_power_map_batch_dev(bflk_group *g, const float *const *stream_dev, int64_t n_samples, int32_t n_frames,
+                                   float *const *power_all_dev);
+int bflk_group_synchronize(bflk_group *g);
 
 /* ---- dynamic steering (MISO) --------------------------------------------------------------------- */
 /* For each target t: steer(theta[t], phi[t]); audio_out[t][N] = Particle::das; power_out[t] = Particle::beam.

@@ -166,3 +166,68 @@ def test_frame_groups_and_bench_batch_rule():
         nf = shard.frame_shard(592, gf, 0)[1]
         ctas = (nf // 2) * -(-(1024 // gd // 4) // 16)
         assert ctas % 148 == 0
+
+
+# ---- the plan the LIBRARY uses (bflk_shard_plan through the C ABI; pure host arithmetic, no GPU) -------------------------
+def test_c_abi_shard_plan_matches_host_logic():
+    import bflk
+    from bflk import shard
+    for D in (1, 7, 35, 1024, 1025, 65536):
+        for B in (1, 2, 7, 592, 593):
+            for world in (1, 2, 3, 4, 8):
+                for gd in [0] + [g for g in (1, 2, 3, 4, 8) if world % g == 0]:
+                    egd, egf = shard.grid_2d(world, gd)
+                    cover = np.zeros((B, D), np.int32)
+                    for r in range(world):
+                        d0, dc, f0, fc = bflk.shard_plan(D, B, world, r, gd)
+                        assert (d0, dc) == shard.direction_shard(D, egd, r % egd)
+                        assert (f0, fc) == shard.frame_shard(B, egf, r // egd)
+                        cover[f0:f0 + fc, d0:d0 + dc] += 1
+                    assert np.all(cover == 1)                       # every (frame, direction) computed exactly once
+    with pytest.raises(bflk.BflkError):
+        bflk.shard_plan(1024, 16, 8, 0, 3)                          # 3 direction groups do not divide 8 ranks
+    with pytest.raises(bflk.BflkError):
+        bflk.shard_plan(1024, 16, 4, 4, 0)                          # rank out of range
+
+
+def _abi_plan_worker(rank, world, port, gd, rows, cols, B, out_path):
+    """World-size-N job whose per-rank slice comes from the C ABI (bflk_shard_plan); the CPU oracle stands in for the
+    kernel, gloo for NCCL; the gathered slices are assembled exactly like multi.cu's assemble_kernel does."""
+    import sys
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import bflk
+    from bflk import synth
+    from oracle import oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyz = O.create_antenna()
+    off, fr = O.mimo_lut(xyz, rows, cols, 180.0)
+    D = rows * cols
+    stream = synth.make_stream(synth.tile_geometry(cases.origins(1, 1)), (B - 1) * 256 + 1024)
+    plans = [bflk.shard_plan(D, B, world, r, gd) for r in range(world)]
+    d0, dc, f0, fc = plans[rank]
+    per, nf = max(p[1] for p in plans), max(p[3] for p in plans)
+    local = torch.zeros((nf, per), dtype=torch.float32)
+    for b in range(fc):
+        w = np.ascontiguousarray(stream[:, (f0 + b) * 256: (f0 + b) * 256 + 1024])
+        local[b, :dc] = torch.from_numpy(O.mimo_update(w, off[d0:d0 + dc], fr[d0:d0 + dc]))
+    gathered = torch.empty((world, nf, per), dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered.view(world * nf, per), local)
+    full = torch.zeros((B, D))
+    for r, (rd0, rdc, rf0, rfc) in enumerate(plans):
+        full[rf0:rf0 + rfc, rd0:rd0 + rdc] = gathered[r, :rfc, :rdc]
+    if rank == 0:
+        ref = np.stack([O.mimo_update(np.ascontiguousarray(stream[:, b * 256: b * 256 + 1024]), off, fr) for b in range(B)])
+        np.save(out_path, np.stack([full.numpy(), ref]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,gd,rows,cols,B", [(2, 0, 6, 6, 4), (2, 1, 5, 7, 3), (4, 2, 4, 5, 5)])
+def test_world_size_n_job_through_the_c_abi_plan(tmp_path, world, gd, rows, cols, B):
+    out = str(tmp_path / "maps.npy")
+    mp.spawn(_abi_plan_worker, args=(world, _free_port(), gd, rows, cols, B, out), nprocs=world, join=True)
+    full, ref = np.load(out)
+    assert np.array_equal(full, ref)
