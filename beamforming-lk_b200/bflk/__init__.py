@@ -31,7 +31,7 @@ SYMBOLS = [
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
-    "bflk_kernel_time_ms", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
+    "bflk_kernel_time_ms", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
     "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded",
@@ -94,6 +94,8 @@ def load_library():
     L.bflk_get_kernel.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.bflk_enable_timing.argtypes = [vp, i32]
     L.bflk_kernel_time_ms.argtypes = [vp, C.POINTER(f32), C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
+    L.bflk_set_window.argtypes = [vp, vp]
+    L.bflk_set_window_dev.argtypes = [vp, vp]
     L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.bflk_miso_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     L.bflk_monopulse.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
@@ -333,15 +335,26 @@ class Beamformer:
         self._check(self._L.bflk_power_map_batch_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
                                                      C.c_void_p(power_dev_ptr), C.c_void_p(cuda_stream)))
 
-    def miso(self, theta, phi, window, want_audio=True, want_power=True):
-        """Particle::steer + das + beam for T targets: returns (audio [T][N] | None, power [T] | None)."""
-        theta, phi = _np(theta, np.float64).ravel(), _np(phi, np.float64).ravel()
+    def set_window(self, window):
+        """Keep window [C][W] on the device: miso() / monopulse() with window=None then work on it (None forgets it)."""
+        if window is None:
+            self._check(self._L.bflk_set_window(self._h, None))
+            return
         window = _np(window, np.float32)
         assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
+        self._check(self._L.bflk_set_window(self._h, _ptr(window)))
+
+    def miso(self, theta, phi, window=None, want_audio=True, want_power=True):
+        """Particle::steer + das + beam for T targets: returns (audio [T][N] | None, power [T] | None).
+        window=None: the window kept on the device by set_window()."""
+        theta, phi = _np(theta, np.float64).ravel(), _np(phi, np.float64).ravel()
+        if window is not None:
+            window = _np(window, np.float32)
+            assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
         T = theta.shape[0]
         audio = np.zeros((T, self.frame_len), np.float32) if want_audio else None
         power = np.zeros(T, np.float32) if want_power else None
-        self._check(self._L.bflk_miso(self._h, _ptr(theta), _ptr(phi), T, _ptr(window),
+        self._check(self._L.bflk_miso(self._h, _ptr(theta), _ptr(phi), T, _ptr(window) if window is not None else None,
                                       _ptr(audio) if want_audio else None, _ptr(power) if want_power else None))
         return audio, power
 
@@ -353,17 +366,18 @@ class Beamformer:
         coeffs = _np(coeffs, np.float32)
         self._check(self._L.bflk_set_fir(self._h, _ptr(coeffs), coeffs.shape[0], coeffs.shape[1]))
 
-    def monopulse(self, theta, phi, window, spread, theta_limit, reference=0.0):
+    def monopulse(self, theta, phi, window, spread, theta_limit, reference=0.0):  # window=None: the resident window
         """GradientParticle::findNearby + the beam part of step() for P particles: returns (theta' [P], near_theta [P][4],
         near_phi [P][4], q [P][4], gradient [P][3] = (theta, phi, radius), error [P])."""
         theta, phi = _np(theta, np.float64).ravel().copy(), _np(phi, np.float64).ravel()
-        window = _np(window, np.float32)
-        assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
+        if window is not None:
+            window = _np(window, np.float32)
+            assert window.shape == (self.n_channels, self.cfg.window_len), window.shape
         P = theta.shape[0]
         nth, nph, q = np.zeros((P, 4)), np.zeros((P, 4)), np.zeros((P, 4))
         grad, err = np.zeros((P, 3)), np.zeros(P)
         self._check(self._L.bflk_monopulse(self._h, _ptr(theta), _ptr(phi), P, C.c_double(spread), C.c_double(theta_limit),
-                                           C.c_double(reference), _ptr(window), _ptr(nth), _ptr(nph), _ptr(q), _ptr(grad), _ptr(err)))
+                                           C.c_double(reference), _ptr(window) if window is not None else None, _ptr(nth), _ptr(nph), _ptr(q), _ptr(grad), _ptr(err)))
         return theta, nth, nph, q, grad, err
 
     # -- neighbours ---------------------------------------------------------------------------------------------

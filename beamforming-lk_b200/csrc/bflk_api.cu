@@ -92,7 +92,9 @@ int bflk_destroy(bflk_handle *h) {
     h->d_fir.release(); h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
-    h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release();
+    h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release(); h->p_stage.release();
+    h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
+    if (h->caller_event) cudaEventDestroy(h->caller_event);
     delete h;
     return BFLK_OK;
 }
@@ -426,6 +428,7 @@ int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
 // the last step has succeeded, so a failed build is retried (and reported again) by the next call.
 int ensure_tiles(bflk_handle *h, int fast) {
     if (h->tiles_valid && h->tiles_fast == fast) return BFLK_OK;
+    if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));   // a queued kernel may still read the old tables
     h->tiles_valid = false;
     h->tiles_fast = fast;
     h->tiles_usable = false;
@@ -498,6 +501,7 @@ extern "C" {
 // Builds (once per grid / mask / range) the direction tiles and per-lane tables of the lane-broadcast kernel.
 static int ensure_bcast(bflk_handle *h) {
     if (h->bcast_valid) return BFLK_OK;
+    if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));   // a queued kernel may still read the old tables
     const int first = h->dir_first, count = h->dir_count;
     std::vector<int32_t> globals;
     if (h->rows > 0 && h->cols > 0) {
@@ -560,6 +564,17 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
                        (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    // the packed rows, partial sums and tables are the handle's: a call on another stream than the previous one waits for it
+    if (h->caller_event && h->last_stream != st) BFLK_CUDA(h, cudaStreamWaitEvent(st, h->caller_event, 0));
+    struct Mark {   // every exit after this point leaves an event behind on the stream the call used
+        bflk_handle *h;
+        cudaStream_t st;
+        ~Mark() {
+            if (!h->caller_event && cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming) != cudaSuccess) return;
+            cudaEventRecord(h->caller_event, st);
+            h->last_stream = st;
+        }
+    } mark{h, st};
     const int N = h->cfg.frame_len, C = h->cfg.n_channels, usable = (int)h->index.size();
     const float norm = static_cast<float>(N * usable);  // power /= float(N_SAMPLES * count), mimo.cpp:137
     // automatic choice: register-tiled kernel when the grid tiles (2x2 direction tiles with small offset
@@ -787,21 +802,112 @@ int bflk_power_map(bflk_handle *h, const float *window, float *power_out) {
 }
 
 // ---- MISO ---------------------------------------------------------------------------------------------------
+// The window can live on the device across calls (the tracker evaluates many steps on one frame,
+// src/dsp/gradient_ascend.cpp:301-409): bflk_set_window uploads it once, bflk_set_window_dev borrows a device buffer.
+int bflk_set_window(bflk_handle *h, const float *window) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!window) {
+        h->resident_window = nullptr;
+        return BFLK_OK;
+    }
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t n_in = (size_t)h->cfg.n_channels * h->cfg.window_len;
+    BFLK_CUDA(h, h->d_resident.reserve(n_in));
+    if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));   // a caller's stream may still read the old one
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_resident.p, window, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->resident_window = h->d_resident.p;
+    return BFLK_OK;
+}
+
+int bflk_set_window_dev(bflk_handle *h, const float *window_dev) {
+    if (!h) return BFLK_ERR_INVALID;
+    h->resident_window = window_dev;
+    return BFLK_OK;
+}
+
+// One launch on `st`.  Up to kMisoInline directions travel in the kernel's parameter space; more go through the pinned
+// trig staging, whose reuse (and that of the device scratch) is ordered against a caller's stream by caller_event.
+// flag_dev receives the call's epoch if a delay exceeds the history.
+static int miso_launch(bflk_handle *h, const double *theta, const double *phi, int n_targets, const float *window_dev,
+                       float *audio_dev, float *power_dev, int32_t *flag_dev, cudaStream_t st) {
+    const int C = h->cfg.n_channels, N = h->cfg.frame_len;
+    if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+    MisoArgs a{};
+    if (n_targets <= kMisoInline) {
+        for (int i = 0; i < n_targets; i++) a.trig_inline[i] = make_trig(theta[i], phi[i]);
+        a.n_inline = n_targets;
+    } else {
+        BFLK_CUDA(h, h->p_trig.reserve(n_targets));
+        BFLK_CUDA(h, h->d_trig.reserve(n_targets));
+        BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));   // the previous call's copy is done with the staging
+        for (int i = 0; i < n_targets; i++) h->p_trig.p[i] = make_trig(theta[i], phi[i]);
+        BFLK_CUDA(h, cudaMemcpyAsync(h->d_trig.p, h->p_trig.p, n_targets * sizeof(DirTrig), cudaMemcpyHostToDevice, st));
+        a.trig = h->d_trig.p;
+    }
+    if (power_dev) {
+        const size_t slots = (size_t)n_targets * das_miso_slices(N);
+        if (slots > h->d_miso_partial.n || (size_t)n_targets > h->d_miso_counters.n) {
+            BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));
+            BFLK_CUDA(h, h->d_miso_partial.reserve(slots));
+            const size_t had = h->d_miso_counters.n;
+            BFLK_CUDA(h, h->d_miso_counters.reserve(std::max<size_t>(n_targets, 256)));
+            if (h->d_miso_counters.n != had) BFLK_CUDA(h, cudaMemsetAsync(h->d_miso_counters.p, 0, h->d_miso_counters.n * sizeof(unsigned), st));
+        }
+        a.partial = h->d_miso_partial.p;
+        a.counters = h->d_miso_counters.p;
+    }
+    a.window = window_dev;
+    a.row_stride = h->cfg.window_len;
+    a.n_frames = 1;
+    a.frame_len = N;
+    a.frame_stride = N;
+    a.xyz = h->d_xyz.p;
+    a.C = C;
+    a.index = h->d_index.p;
+    a.usable = (int)h->index.size();
+    a.k_scale = delay_scale(h);
+    a.history = h->cfg.history;
+    a.n_targets = n_targets;
+    a.audio = audio_dev;
+    a.power = power_dev;
+    a.norm = static_cast<float>(N);  // Particle::beam: power_accumulator /= N_SAMPLES, particle.cpp:79
+    a.error_flag = flag_dev;
+    a.epoch = ++h->miso_epoch;
+    if (h->miso_epoch == 0x7fffffff) h->miso_epoch = 0;
+    BFLK_CUDA(h, launch_das_miso(a, st));
+    BFLK_CUDA(h, cudaEventRecord(h->caller_event, st));
+    h->launches++;
+    return BFLK_OK;
+}
+
 int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window_dev,
                   float *audio_dev, float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_geometry) return h->fail(BFLK_ERR_STATE, "bflk_miso: set the geometry first");
-    if (!theta || !phi || n_targets <= 0 || !window_dev) return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments");
+    if (!window_dev) window_dev = h->resident_window;
+    if (!theta || !phi || n_targets <= 0 || !window_dev) return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments (no window given and none resident)");
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->fir_phases == 0) {
+        if (h->d_miso_out.n == 0) {
+            BFLK_CUDA(h, h->d_miso_out.reserve(1));
+            BFLK_CUDA(h, cudaMemsetAsync(h->d_miso_out.p, 0, sizeof(float), st));
+        }
+        return miso_launch(h, theta, phi, n_targets, window_dev, audio_dev, power_dev, reinterpret_cast<int32_t *>(h->d_miso_out.p), st);
+    }
+    // FIR interpolation (bflk_set_fir): tables through the table kernel, then the generic kernel
     const int C = h->cfg.n_channels, N = h->cfg.frame_len;
     const size_t TC = (size_t)n_targets * C;
     BFLK_CUDA(h, h->d_soff.reserve(TC));
     BFLK_CUDA(h, h->d_sfrac.reserve(TC));
+    if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));
     int32_t max_delay = 0;
     int rc = run_steer_tables(h, theta, phi, n_targets, h->d_soff.p, h->d_sfrac.p, &max_delay);  // Particle::steer
     if (rc) return rc;
     if ((rc = check_delay_range(h, max_delay, "bflk_miso"))) return rc;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->cfg.window_len < h->cfg.history + N + h->fir_taps - 1)
+        return h->fail(BFLK_ERR_INVALID, "bflk_miso: the window is too short for the FIR taps");
     GenericArgs a{};
     a.stream = window_dev;
     a.row_stride = h->cfg.window_len;
@@ -816,13 +922,11 @@ int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_
     a.n_dir = n_targets;
     a.power = power_dev;
     a.audio = audio_dev;
-    a.norm = static_cast<float>(N);  // Particle::beam: power_accumulator /= N_SAMPLES, particle.cpp:79
-    if (h->fir_phases > 0) {
-        if (h->cfg.window_len < h->cfg.history + N + h->fir_taps - 1)
-            return h->fail(BFLK_ERR_INVALID, "bflk_miso: the window is too short for the FIR taps");
-        a.fir = h->d_fir.p; a.fir_phases = h->fir_phases; a.fir_taps = h->fir_taps;
-    }
+    a.norm = static_cast<float>(N);
+    a.fir = h->d_fir.p; a.fir_phases = h->fir_phases; a.fir_taps = h->fir_taps;
     BFLK_CUDA(h, launch_das_generic(a, st));
+    if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+    BFLK_CUDA(h, cudaEventRecord(h->caller_event, st));
     h->launches++;
     return BFLK_OK;
 }
@@ -830,21 +934,44 @@ int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_
 int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window,
               float *audio_out, float *power_out) {
     if (!h) return BFLK_ERR_INVALID;
-    if (!window || n_targets <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments");
+    if (!h->have_geometry) return h->fail(BFLK_ERR_STATE, "bflk_miso: set the geometry first");
+    if (!theta || !phi || n_targets <= 0 || (!window && !h->resident_window))
+        return h->fail(BFLK_ERR_INVALID, "bflk_miso: null / empty arguments (no window given and none resident)");
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int N = h->cfg.frame_len;
     const size_t n_in = (size_t)h->cfg.n_channels * h->cfg.window_len;
-    BFLK_CUDA(h, h->d_window.reserve(n_in));
-    BFLK_CUDA(h, h->d_audio.reserve((size_t)n_targets * h->cfg.frame_len));
-    BFLK_CUDA(h, h->d_power.reserve(n_targets));
-    BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, window, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    int rc = bflk_miso_dev(h, theta, phi, n_targets, h->d_window.p, audio_out ? h->d_audio.p : nullptr,
-                           power_out ? h->d_power.p : nullptr, h->stream);
+    const float *wdev = h->resident_window;
+    if (window) {
+        BFLK_CUDA(h, h->d_window.reserve(n_in));
+        if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));
+        BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, window, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        wdev = h->d_window.p;
+    }
+    // device output block [flag | audio | power] -> ONE copy into pinned staging -> the caller's buffers
+    const size_t n_audio = audio_out ? (size_t)n_targets * N : 0, n_power = power_out ? n_targets : 0, n_all = 1 + n_audio + n_power;
+    if (n_all > h->d_miso_out.n) {
+        if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));
+        BFLK_CUDA(h, h->d_miso_out.reserve(n_all));
+        BFLK_CUDA(h, cudaMemsetAsync(h->d_miso_out.p, 0, sizeof(float), h->stream));   // the range flag starts clear
+    }
+    BFLK_CUDA(h, h->p_stage.reserve(n_all));
+    float *d_audio = h->d_miso_out.p + 1, *d_power = d_audio + n_audio;
+    int rc;
+    if (h->fir_phases == 0) {
+        rc = miso_launch(h, theta, phi, n_targets, wdev, audio_out ? d_audio : nullptr, power_out ? d_power : nullptr,
+                         reinterpret_cast<int32_t *>(h->d_miso_out.p), h->stream);
+    } else {
+        rc = bflk_miso_dev(h, theta, phi, n_targets, wdev, audio_out ? d_audio : nullptr, power_out ? d_power : nullptr, h->stream);
+    }
     if (rc) return rc;
-    if (audio_out)
-        BFLK_CUDA(h, cudaMemcpyAsync(audio_out, h->d_audio.p, (size_t)n_targets * h->cfg.frame_len * sizeof(float),
-                                     cudaMemcpyDeviceToHost, h->stream));
-    if (power_out) BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_targets * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_stage.p, h->d_miso_out.p, n_all * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    int32_t flag;
+    std::memcpy(&flag, h->p_stage.p, sizeof(flag));
+    if (h->fir_phases == 0 && flag == h->miso_epoch)
+        return h->fail(BFLK_ERR_RANGE, "bflk_miso: a steering delay exceeds history %d", h->cfg.history);
+    if (audio_out) std::memcpy(audio_out, h->p_stage.p + 1, n_audio * sizeof(float));
+    if (power_out) std::memcpy(power_out, h->p_stage.p + 1 + n_audio, n_power * sizeof(float));
     return BFLK_OK;
 }
 
@@ -906,7 +1033,8 @@ int bflk_monopulse(bflk_handle *h, double *theta, const double *phi, int32_t n_p
                    double theta_limit, double reference, const float *window, double *near_theta, double *near_phi,
                    double *q, double *gradient, double *error) {
     if (!h) return BFLK_ERR_INVALID;
-    if (!theta || !phi || n_particles <= 0 || !window) return h->fail(BFLK_ERR_INVALID, "bflk_monopulse: null / empty arguments");
+    if (!theta || !phi || n_particles <= 0 || (!window && !h->resident_window))
+        return h->fail(BFLK_ERR_INVALID, "bflk_monopulse: null / empty arguments (no window given and none resident)");
     const int T = 4 * n_particles;
     std::vector<double> nth(T), nph(T);
     for (int p = 0; p < n_particles; p++) quadrant_directions(&theta[p], phi[p], spread, theta_limit, &nth[4 * p], &nph[4 * p]);

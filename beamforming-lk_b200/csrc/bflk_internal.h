@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -195,6 +196,17 @@ struct bflk_handle {
     bflk::DevBuf<float> d_fir;
     int32_t fir_phases = 0, fir_taps = 0;
 
+    // window kept on the device across calls (bflk_set_window): MISO / monopulse iterations on one frame do not re-upload it
+    const float *resident_window = nullptr;   // d_resident.p, or a caller-owned device pointer (bflk_set_window_dev)
+    bflk::DevBuf<float> d_resident;
+    bflk::DevBuf<float> d_miso_out;           // [flag | audio | power]: one D2H copy per call
+    bflk::DevBuf<float> d_miso_partial;
+    bflk::DevBuf<unsigned> d_miso_counters;
+    int32_t miso_epoch = 0;
+    bflk::PinBuf<float> p_stage;              // pinned staging of single-frame inputs / small outputs
+    cudaEvent_t caller_event = nullptr;       // orders work the library puts on a caller's stream against the handle's scratch
+    cudaStream_t last_stream = nullptr;       // stream of the last asynchronous call
+
     // scratch
     bflk::DevBuf<float> d_window, d_power, d_audio, d_partial;
     bflk::DevBuf<bflk::DirTrig> d_trig;
@@ -265,6 +277,35 @@ struct GenericArgs {
     int fir_phases = 0, fir_taps = 0;
 };
 cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st);
+
+// ---- das_miso.cu ------------------------------------------------------------------------------------
+constexpr int kMisoInline = 128;   // targets whose DirTrig travel in the kernel's parameter space (no H2D copy)
+struct MisoArgs {
+    const float *window;     // [C][row_stride]; frame b starts at window + b * frame_stride
+    int64_t row_stride;
+    int n_frames, frame_len, frame_stride;
+    const DirTrig *trig;     // [n_targets] on the device (used when n_inline == 0)
+    const float *xyz;        // [C][3]
+    int C;
+    const int32_t *index;    // [usable]
+    int usable;
+    float k_scale;           // float(sample_rate / propagation_speed)
+    int history;
+    int n_targets;
+    float *audio;            // [B][T][N] or nullptr
+    float *power;            // [B][T] or nullptr
+    float *partial;          // [B][T][slices] scratch of the power reduction (power != nullptr)
+    unsigned *counters;      // [B][T] zero-initialised, self-resetting arrival counters (power != nullptr)
+    float norm;              // N (Particle::beam)
+    int32_t *error_flag;     // set to `epoch` when a delay exceeds the history
+    int32_t epoch;
+    int32_t *off_out;        // optional [T][C] tables as built (nullptr: not stored)
+    float *frac_out;
+    int n_inline;            // n_targets when the directions are in trig_inline, else 0
+    DirTrig trig_inline[kMisoInline];
+};
+cudaError_t launch_das_miso(const MisoArgs &a, cudaStream_t st);
+int das_miso_slices(int frame_len);
 
 // ---- das_tile.cu ------------------------------------------------------------------------------------
 struct TileArgs {

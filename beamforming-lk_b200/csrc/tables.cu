@@ -7,17 +7,9 @@
 // only correctly-rounded float mul / fma / sub with every rounding pinned (__f*_rn), so the tables are
 // bit-identical to the host restatement in oracle/oracle.c.
 #include "bflk_internal.h"
+#include "steer.cuh"
 
 namespace bflk {
-
-__device__ __forceinline__ float steer_z(const DirTrig t, float px, float py, float pz) {
-    // rotateZ(float(phi)) * p, k = 0,1,2 from a zero accumulator (documented evaluation order)
-    float xr = __fmaf_rn(0.0f, pz, __fmaf_rn(-t.sz, py, __fmaf_rn(t.cz, px, 0.0f)));
-    float yr = __fmaf_rn(0.0f, pz, __fmaf_rn(t.cz, py, __fmaf_rn(t.sz, px, 0.0f)));
-    float zr = __fmaf_rn(1.0f, pz, __fmaf_rn(0.0f, py, __fmaf_rn(0.0f, px, 0.0f)));
-    // row Z of rotateY(-float(theta)): (-sin, 0, cos)
-    return __fmaf_rn(t.cy, zr, __fmaf_rn(0.0f, yr, __fmaf_rn(-t.sy, xr, 0.0f)));
-}
 
 __global__ void __launch_bounds__(128) steer_tables_kernel(const DirTrig *__restrict__ trig, const float *__restrict__ xyz,
                                                            int C, float k_scale, int history, int32_t *__restrict__ off,

@@ -173,10 +173,21 @@ int bflk_group_power_map_batch_dev(bflk_group *g, const float *const *stream_dev
 int bflk_group_synchronize(bflk_group *g);
 
 /* ---- dynamic steering (MISO) --------------------------------------------------------------------- */
+/* Keep one frame's window[C][W] on the device across calls: the tracker evaluates many steps on the same frame
+ * (src/dsp/gradient_ascend.cpp:301-409), and bflk_miso / bflk_monopulse with window == NULL use it instead of uploading
+ * 4 * C * W bytes every time.  bflk_set_window copies a host buffer (NULL forgets it); bflk_set_window_dev borrows a
+ * device buffer the caller keeps alive. */
+int bflk_set_window(bflk_handle *h, const float *window);
+int bflk_set_window_dev(bflk_handle *h, const float *window_dev);
 /* For each target t: steer(theta[t], phi[t]); audio_out[t][N] = Particle::das; power_out[t] = Particle::beam.
- * Either output may be NULL. window[C][W] as in bflk_power_map. */
+ * Either output may be NULL. window[C][W] as in bflk_power_map, or NULL = the resident window.  One kernel launch:
+ * the steering tables are built inside it (same bits as bflk_steer_tables); a delay beyond the history makes the
+ * call return BFLK_ERR_RANGE. */
 int bflk_miso(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets, const float *window,
               float *audio_out, float *power_out);
+/* Device pointers, asynchronous on cuda_stream (NULL = the handle's stream); window_dev == NULL = the resident window.
+ * Being asynchronous it cannot return BFLK_ERR_RANGE: a delay beyond the history is clamped to it (validate the
+ * directions once with bflk_steer_tables, or use bflk_miso). */
 int bflk_miso_dev(bflk_handle *h, const double *theta, const double *phi, int32_t n_targets,
                   const float *window_dev, float *audio_dev, float *power_dev, void *cuda_stream);
 

@@ -291,6 +291,46 @@ def test_cfg4_miso_vs_oracle(bf, oracle):
         assert abs(power[t] - oracle.particle_beam(window, off[t], fr[t])) <= POWER_RTOL * power[t]
 
 
+def test_miso_resident_window_many_targets_masks_and_range(bf, oracle):
+    """The fused MISO kernel (tables built in the kernel): a window kept on the device across calls, more targets than
+    SMs, a channel mask, repeated calls, and the range check the host path used to do (delay beyond the history)."""
+    c = cases.CFG4
+    w = bf.MISOWorker(cases.origins(c["nx"], c["ny"]))
+    window = _synth_window(bf, c)
+    xyz = oracle.create_tiled_antenna(cases.origins(c["nx"], c["ny"]))
+    rng = np.random.default_rng(21)
+    T = 300
+    th, ph = rng.random(T) * np.deg2rad(85.0), rng.random(T) * 2 * np.pi
+    off, fr = oracle.steer_tables(xyz, th, ph)
+    w.set_window(window)
+    audio, power = w.miso(th, ph)                                   # window=None: the resident one
+    for t in range(0, T, 17):
+        assert np.array_equal(audio[t].view(np.uint32), oracle.particle_das(window, off[t], fr[t]).view(np.uint32))
+        assert abs(power[t] - oracle.particle_beam(window, off[t], fr[t])) <= POWER_RTOL * power[t]
+    a2, p2 = w.miso(th, ph, window)                                 # explicit window: same bits
+    assert np.array_equal(a2, audio) and np.array_equal(p2, power)
+    window2 = (window * np.float32(0.5)).astype(np.float32)
+    a3, _ = w.miso(th[:5], ph[:5], window2)                         # an explicit window does not replace the resident one
+    a4, _ = w.miso(th[:5], ph[:5])
+    assert np.array_equal(a4, audio[:5]) and not np.array_equal(a3, a4)
+    mask = np.arange(3, 512, 5, dtype=np.int32)
+    w.set_channel_mask(mask)
+    am, pm = w.miso(th[:9], ph[:9])
+    for t in range(9):
+        assert np.array_equal(am[t].view(np.uint32), oracle.particle_das(window, off[t], fr[t], index=mask).view(np.uint32))
+        assert abs(pm[t] - oracle.particle_beam(window, off[t], fr[t], index=mask)) <= POWER_RTOL * pm[t]
+    w.set_window(None)
+    with pytest.raises(bf.BflkError):
+        w.miso(th[:2], ph[:2])                                      # nothing resident, nothing given
+    # 8 arrays in a row would need ~180 samples of delay: with history 64 the kernel raises the range flag
+    short = bf.MISOWorker(cases.origins(8, 1), history=64, window_len=512)
+    with pytest.raises(bf.BflkError) as e:
+        short.miso([np.deg2rad(80.0)], [0.0], np.zeros((512, 512), np.float32))
+    assert e.value.code == -5
+    ok_audio, _ = short.miso([0.0], [0.0], np.ones((512, 512), np.float32))   # boresight: zero delays, fine
+    assert np.all(ok_audio == 512.0)
+
+
 def test_monopulse_step_vs_oracle(bf, oracle):
     """f2: quadrant directions bit-exact, the 4 x P beam powers within 1e-4, gradient and error from them."""
     c = cases.CFG4

@@ -42,3 +42,7 @@ rng = np.random.default_rng(5)
 pth, pph = rng.random(P) * np.deg2rad(70.0), rng.random(P) * 2 * np.pi
 print("f2: bflk_monopulse, 26 particles x 4 beams x 512 mics (quadrant directions, tables, beams, gradient): "
       + timeit(lambda: m.monopulse(pth, pph, win, np.deg2rad(4.0), np.deg2rad(80.0), 3e-4)))
+m.set_window(win)
+print("cfg4: bflk_miso on the RESIDENT window (bflk_set_window once per frame), 16 targets: " + timeit(lambda: m.miso(th, ph)))
+print("f2: bflk_monopulse on the resident window, 26 particles x 4 beams: "
+      + timeit(lambda: m.monopulse(pth, pph, None, np.deg2rad(4.0), np.deg2rad(80.0), 3e-4)))
