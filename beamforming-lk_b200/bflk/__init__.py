@@ -31,7 +31,7 @@ SYMBOLS = [
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
-    "bflk_kernel_time_ms", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
+    "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
     "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded",
@@ -94,6 +94,7 @@ def load_library():
     L.bflk_get_kernel.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.bflk_enable_timing.argtypes = [vp, i32]
     L.bflk_kernel_time_ms.argtypes = [vp, C.POINTER(f32), C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
+    L.bflk_fp32_peak_tflops.argtypes = [vp, C.POINTER(f32)]
     L.bflk_set_window.argtypes = [vp, vp]
     L.bflk_set_window_dev.argtypes = [vp, vp]
     L.bflk_miso.argtypes = [vp, vp, vp, i32, vp, vp, vp]
@@ -230,6 +231,12 @@ class Beamformer:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self._L.bflk_get_kernel(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def fp32_peak_tflops(self):
+        """TFLOP/s of a packed-FMA saturation kernel on this device (empirical FP32 roofline)."""
+        v = C.c_float()
+        self._check(self._L.bflk_fp32_peak_tflops(self._h, C.byref(v)))
+        return v.value
 
     def enable_timing(self, on=True):
         self._check(self._L.bflk_enable_timing(self._h, 1 if on else 0))

@@ -389,6 +389,32 @@ static void timing_hook(void *ctx, int kind, bool begin, cudaStream_t st) {
     }
 }
 
+int bflk_fp32_peak_tflops(bflk_handle *h, float *tflops) {
+    if (!h || !tflops) return BFLK_ERR_INVALID;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int blocks = h->sm_count, iters = 8192;
+    BFLK_CUDA(h, h->d_power.reserve((size_t)blocks * 512));
+    cudaEvent_t e0, e1;
+    BFLK_CUDA(h, cudaEventCreate(&e0));
+    BFLK_CUDA(h, cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; rep++) {   // first launch warms up; best of the rest
+        BFLK_CUDA(h, cudaEventRecord(e0, h->stream));
+        BFLK_CUDA(h, launch_ffma2_peak(h->d_power.p, blocks, iters, h->stream));
+        BFLK_CUDA(h, cudaEventRecord(e1, h->stream));
+        BFLK_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        BFLK_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        h->launches++;
+        const double flop = (double)blocks * 512 * iters * 16 * 4;   // a packed FMA = 2 lanes x 2 FLOP
+        if (rep > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return BFLK_OK;
+}
+
 int bflk_enable_timing(bflk_handle *h, int32_t on) {
     if (!h) return BFLK_ERR_INVALID;
     h->timing = on != 0;

@@ -367,6 +367,7 @@ cudaError_t launch_das_bcast(const BcastArgs &a, cudaStream_t st, int *launches,
 cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t *d_argmax, float *d_max, cudaStream_t st);
 cudaError_t launch_channel_power(const float *d_signals, int n_ch, int W, float *d_power, cudaStream_t st);
 cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *d_exposure, cudaStream_t st);
+cudaError_t launch_ffma2_peak(float *d_out, int n_blocks, int iters, cudaStream_t st);
 
 // ---- bflk_api.cu internals used by multi.cu ---------------------------------------------------------------
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold n_samples valid samples

@@ -101,4 +101,32 @@ cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *
     return cudaGetLastError();
 }
 
+// ---- FP32 saturation micro-benchmark (the empirical roofline denominator) -------------------------------
+// 16 independent packed-FMA chains per thread, 16 warps per SM, one CTA per SM: what the FP32 pipe delivers on this chip
+// at the clock it runs at under load (tools/ubench measures the same: 127.6 of 128 lane-operations per clock per SM).
+__global__ void __launch_bounds__(512) ffma2_peak_kernel(float *out, int iters, float seed) {
+    unsigned long long p[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float v = seed + (float)(i + threadIdx.x);
+        p[i] = ((unsigned long long)__float_as_uint(v) << 32) | __float_as_uint(v * 0.5f);
+    }
+    const float f = seed * 0.999f, g = seed * 1e-3f;
+    const unsigned long long f2 = ((unsigned long long)__float_as_uint(f) << 32) | __float_as_uint(f);
+    const unsigned long long g2 = ((unsigned long long)__float_as_uint(g) << 32) | __float_as_uint(g);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(f2), "l"(g2));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += __uint_as_float((unsigned)p[i]) + __uint_as_float((unsigned)(p[i] >> 32));
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t launch_ffma2_peak(float *d_out, int n_blocks, int iters, cudaStream_t st) {
+    ffma2_peak_kernel<<<n_blocks, 512, 0, st>>>(d_out, iters, 1.0f);
+    return cudaGetLastError();
+}
+
 }  // namespace bflk

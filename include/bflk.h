@@ -124,6 +124,9 @@ int64_t bflk_launch_count(const bflk_handle *h);
  * bflk_kernel_time_ms synchronises on those events, returns the accumulated milliseconds and launch
  * counts since the last call, and resets the accumulators. */
 int bflk_enable_timing(bflk_handle *h, int32_t on);
+/* FP32 throughput a packed-FMA saturation kernel reaches on this device right now (TFLOP/s, ~10 ms): the empirical
+ * denominator reported next to the nominal FP32 roofline. */
+int bflk_fp32_peak_tflops(bflk_handle *h, float *tflops);
 int bflk_kernel_time_ms(bflk_handle *h, float *das_ms, int32_t *das_launches, float *pack_ms, int32_t *pack_launches);
 
 /* ---- multi-GPU: the grid (x the frames of a batch) sharded across the GPUs of one box ---------------- */
