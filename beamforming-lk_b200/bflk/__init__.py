@@ -29,7 +29,7 @@ SYMBOLS = [
     "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
-    "bflk_power_map_batch",
+    "bflk_power_map_batch", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
@@ -87,6 +87,8 @@ def load_library():
     L.bflk_power_map.argtypes = [vp, vp, vp]
     L.bflk_power_map_i32.argtypes = [vp, vp, vp]
     L.bflk_power_map_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_i32.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_i32_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_set_kernel.argtypes = [vp, i32]
     L.bflk_launch_count.argtypes = [vp]
@@ -325,6 +327,14 @@ class Beamformer:
         self._check(self._L.bflk_power_map_i32(self._h, _ptr(frames), _ptr(out)))
         return out
 
+    def power_map_batch_i32(self, frames, n_frames):
+        """frames [T][C] int32 wire samples (one row per time sample), frame b at row b*N -> power [B][count]."""
+        frames = _np(frames, np.int32)
+        assert frames.shape[1] == self.n_channels
+        out = np.zeros((n_frames, self.n_directions()[2]), np.float32)
+        self._check(self._L.bflk_power_map_batch_i32(self._h, _ptr(frames), frames.shape[0], n_frames, _ptr(out)))
+        return out
+
     def power_map_batch(self, stream, n_frames):
         """stream [C][T] float32 (host), frame b at sample b*N -> power [B][count]."""
         stream = _np(stream, np.float32)
@@ -486,6 +496,14 @@ class Group:
 
     def size(self):
         return int(self._L.bflk_group_size(self._g))
+
+    def power_map_batch_i32(self, frames, n_frames):
+        """frames [T][C] int32 wire samples (one row per time sample), frame b at row b*N -> power [B][count]."""
+        frames = _np(frames, np.int32)
+        assert frames.shape[1] == self.n_channels
+        out = np.zeros((n_frames, self.n_directions()[2]), np.float32)
+        self._check(self._L.bflk_power_map_batch_i32(self._h, _ptr(frames), frames.shape[0], n_frames, _ptr(out)))
+        return out
 
     def power_map_batch(self, stream, n_frames):
         stream = _np(stream, np.float32)

@@ -93,7 +93,7 @@ int bflk_destroy(bflk_handle *h) {
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release(); h->p_stage.release();
-    h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
+    h->d_wire.release(); h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
     if (h->caller_event) cudaEventDestroy(h->caller_event);
     delete h;
     return BFLK_OK;
@@ -584,7 +584,8 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
                         float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
-    if (!stream_dev || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    const int32_t *wire = h->wire_src;   // wire-format call: stream_dev is null, the samples are h->wire_src[n_samples][C]
+    if ((!stream_dev && !wire) || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
     if (n_samples < min_stream_samples(h, n_frames))
         return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
                        (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
@@ -614,10 +615,19 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
         // automatic choice = the two-FMA variant (power within the 1e-4 bar); 2 asks for bit-identical delayed sums
         int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0);
         if (rc) return rc;
-        tiled = h->tiles_usable && !(row_stride & 1) && !((uintptr_t)stream_dev & 7);  // packed rows: 8-byte loads
+        tiled = h->tiles_usable && (wire || (!(row_stride & 1) && !((uintptr_t)stream_dev & 7)));  // packed rows: 8-byte loads
         if (h->kernel_choice != 0 && !tiled)
             return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (offset spread %d of at most %d, %d stage buffers fit shared memory)",
                            h->tile_smax, das_tile_max_span(), h->tile_geom.stages);
+    }
+    if (wire && !tiled) {
+        // the other kernels read channel-major float rows: convert the wire samples first (ingest_kernel), then carry on
+        BFLK_CUDA(h, h->d_window.reserve((size_t)C * (n_samples + 1)));
+        BFLK_CUDA(h, launch_ingest(wire, (int)n_samples, C, h->d_window.p, st));
+        h->launches++;
+        stream_dev = h->d_window.p;
+        row_stride = n_samples;
+        wire = nullptr;
     }
     const bool bcast_ok = N >= 256 && das_bcast_fits(das_bcast_geometry(h->cfg.history, h->max_delay));
     if (h->kernel_choice == 3 && !bcast_ok)
@@ -656,6 +666,8 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
     }
     if (tiled) {
         TileArgs a{};
+        a.wire = wire;
+        a.wire_cols = C;
         a.stream = stream_dev;
         a.row_stride = row_stride;
         a.row_len = n_samples;
@@ -801,25 +813,67 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
     return BFLK_OK;
 }
 
-int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out) {
+// frames[n_samples][C] int32 on the DEVICE, frame b = rows [b * N, b * N + H + N + 1): asynchronous on cuda_stream
+int bflk_power_map_batch_i32_dev(bflk_handle *h, const int32_t *frames_dev, int64_t n_samples, int32_t n_frames,
+                                 float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
-    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map_i32: set geometry and grid first");
-    if (!frames || !power_out) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_i32: null buffer");
-    const int C = h->cfg.n_channels, W = h->cfg.window_len;
-    if (C % 8) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_i32: n_channels must be a multiple of 8 (serpentine rows)");
+    if (!frames_dev) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_i32: null buffer");
+    if (h->cfg.n_channels % 8) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_i32: n_channels must be a multiple of 8 (serpentine rows)");
+    if (n_samples > 0x7fffffff) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_i32: more than 2^31 samples per call");
+    h->wire_src = frames_dev;
+    const int rc = power_map_dev(h, nullptr, n_samples, n_samples, n_frames, power_dev, cuda_stream);
+    h->wire_src = nullptr;
+    return rc;
+}
+
+// Host buffers: the wire samples go up in chunks of frames (contiguous rows of the sample-major layout) on the copy
+// stream while the previous chunk is packed and beamformed.
+int bflk_power_map_batch_i32(bflk_handle *h, const int32_t *frames, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map_batch_i32: set geometry and grid first");
+    if (!frames || !power_out || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_i32: null buffer or no frames");
+    if (n_samples < min_stream_samples(h, n_frames))
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_i32: %lld samples cannot hold %d frames (need %lld)",
+                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
-    const size_t cnt = (size_t)W * C;
-    BFLK_CUDA(h, h->d_misc.reserve(cnt));
-    BFLK_CUDA(h, h->d_window.reserve(cnt));
-    BFLK_CUDA(h, h->d_power.reserve(h->dir_count));
-    BFLK_CUDA(h, cudaMemcpyAsync(h->d_misc.p, frames, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    BFLK_CUDA(h, launch_ingest(h->d_misc.p, W, C, h->d_window.p, h->stream));  // -> window[C][W], exposure layout
-    h->launches++;
-    int rc = power_map_dev(h, h->d_window.p, W, W, 1, h->d_power.p, h->stream);
+    const int C = h->cfg.n_channels, N = h->cfg.frame_len;
+    BFLK_CUDA(h, h->d_wire.reserve((size_t)C * n_samples));
+    BFLK_CUDA(h, h->d_power.reserve((size_t)n_frames * h->dir_count));
+    const int64_t tail = frame_tail_samples(h);
+    int chunk_frames = n_frames;
+    int rc = host_chunk_frames(h, n_frames, &chunk_frames);
     if (rc) return rc;
-    BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, (size_t)h->dir_count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    const int n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    if (!h->copy_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    while ((int)h->chunk_events.size() < n_chunks) {
+        cudaEvent_t e;
+        BFLK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunk_events.push_back(e);
+    }
+    int64_t copied = 0;  // samples (rows) already on the device
+    for (int k = 0; k < n_chunks; k++) {
+        const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
+        const int64_t need = std::min<int64_t>(n_samples, k == n_chunks - 1 ? n_samples : (int64_t)(f0 + nf) * N + tail);
+        if (need > copied) {
+            BFLK_CUDA(h, cudaMemcpyAsync(h->d_wire.p + (size_t)copied * C, frames + (size_t)copied * C, (size_t)(need - copied) * C * sizeof(int32_t),
+                                         cudaMemcpyHostToDevice, h->copy_stream));
+            copied = need;
+        }
+        BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
+        BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
+        float *pk = h->d_power.p + (size_t)f0 * h->dir_count;
+        rc = bflk_power_map_batch_i32_dev(h, h->d_wire.p + (size_t)f0 * N * C, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        if (rc) return rc;
+        BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
+                                     cudaMemcpyDeviceToHost, h->stream));
+    }
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     return BFLK_OK;
+}
+
+int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    return bflk_power_map_batch_i32(h, frames, h->cfg.window_len, 1, power_out);
 }
 
 int bflk_power_map(bflk_handle *h, const float *window, float *power_out) {

@@ -198,6 +198,8 @@ struct bflk_handle {
 
     // window kept on the device across calls (bflk_set_window): MISO / monopulse iterations on one frame do not re-upload it
     const float *resident_window = nullptr;   // d_resident.p, or a caller-owned device pointer (bflk_set_window_dev)
+    const int32_t *wire_src = nullptr;        // set for the duration of a wire-format call: power_map_dev packs from it
+    bflk::DevBuf<int32_t> d_wire;
     bflk::DevBuf<float> d_resident;
     bflk::DevBuf<float> d_miso_out;           // [flag | audio | power]: one D2H copy per call
     bflk::DevBuf<float> d_miso_partial;
@@ -309,6 +311,8 @@ int das_miso_slices(int frame_len);
 
 // ---- das_tile.cu ------------------------------------------------------------------------------------
 struct TileArgs {
+    const int32_t *wire = nullptr;   // when set: sample-major wire frames [row_len][wire_cols] instead of `stream` (pack_wire_kernel)
+    int wire_cols = 0;
     const float *stream;
     int64_t row_stride;
     int64_t row_len;             // valid samples per row from `stream` (chunked host batches pass row_len < row_stride)

@@ -51,6 +51,8 @@ static_assert(sizeof(TileEntry) == 32, "TileEntry is two 16-byte loads");
 
 // ---- pack: stream[C][T] -> packed[pair][usable][row] of float2{A, B} -------------------------------------
 struct PackArgs {
+    const int32_t *wire;  // sample-major wire frames [row_len][wire_cols] (src/fpga/receiver.h:24-30) instead of `stream`
+    int wire_cols;
     const float *stream;
     int64_t row_stride;   // T
     int64_t row_len;      // valid samples per row from the stream pointer (<= row_stride)
@@ -98,6 +100,52 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     if ((ch & 3) == 3 && 16 * (padded_chunk(ch) + 2) <= a.copy_bytes) {
         *reinterpret_cast<float4 *>(dst + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4 *>(dst + a.copy_bytes + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---- pack straight from the wire format ---------------------------------------------------------
+// The FPGA sends one message per time sample: int32 stream[n_sensors], daisy-chained arrays mirrored (receiver.h:24-30).
+// Pipeline::receive_exposure turns that into per-channel float rows on the host (serpentine un-flip, / 2^23,
+// src/fpga/pipeline.cpp:260-297) and MIMOWorker::update copies them again (mimo.cpp:100-103).  Here the conversion,
+// the un-flip (folded into the column index), the transpose and the pair-interleave of pack_kernel are ONE pass: a CTA
+// loads a [130 samples][32 channels] tile of both blocks of a pair with coalesced 128-byte rows, keeps it transposed in
+// shared memory, and writes the same packed rows pack_kernel writes -- so the delay-and-sum kernel is unchanged and its
+// result is bit-identical to the float path (int32 -> float and the power-of-two scale are exact for 24-bit samples).
+constexpr int kWireCh = 32, kWireChunks = 64, kWireT = 2 * kWireChunks + 2, kWirePitch = kWireT + 1;
+
+__global__ void __launch_bounds__(256) pack_wire_kernel(PackArgs a) {
+    __shared__ float sm[2][kWireCh][kWirePitch];
+    const int pair = a.pair0 + blockIdx.z, s0 = blockIdx.y * kWireCh, ch0 = blockIdx.x * kWireChunks;
+    const int itemA = 2 * pair, itemB = min(2 * pair + 1, a.n_items - 1);
+    const int64_t t0[2] = {item_start(itemA, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch0,
+                           item_start(itemB, a.blocks_per_frame, a.frame_len, a.frame_stride) + a.stage_off + 2 * ch0};
+    const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int s = s0 + cl;
+    int col = -1;
+    if (s < a.usable) {
+        const int sensor = a.index[s], grp = sensor >> 3;
+        col = (grp & 1) ? sensor : 8 * (1 + grp) - 1 - (sensor & 7);   // every second group of 8 is mirrored (pipeline.cpp:273-287)
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        for (int t = r; t < kWireT; t += 8) {
+            const int64_t ts = t0[h] + t;
+            float v = 0.f;
+            if (col >= 0 && ts < a.row_len) v = __fdiv_rn((float)a.wire[(size_t)ts * a.wire_cols + col], 8388608.0f);
+            sm[h][cl][t] = v;
+        }
+    __syncthreads();
+    for (int o = threadIdx.x; o < kWireCh * kWireChunks; o += 256) {
+        const int chl = o % kWireChunks, c2 = o / kWireChunks, ch = ch0 + chl;
+        if (ch >= a.row_chunks || s0 + c2 >= a.usable) continue;
+        const float *A = &sm[0][c2][2 * chl], *B = &sm[1][c2][2 * chl];
+        char *dst = reinterpret_cast<char *>(a.packed) + ((size_t)pair * a.usable + s0 + c2) * a.row_bytes + 16 * padded_chunk(ch);
+        *reinterpret_cast<float4 *>(dst) = make_float4(A[0], B[0], A[1], B[1]);
+        *reinterpret_cast<float4 *>(dst + a.copy_bytes) = make_float4(A[1], B[1], A[2], B[2]);
+        if ((ch & 3) == 3 && 16 * (padded_chunk(ch) + 2) <= a.copy_bytes) {
+            *reinterpret_cast<float4 *>(dst + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(dst + a.copy_bytes + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -360,9 +408,11 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     const int nblk = a.frame_len <= kBlock ? 1 : (a.frame_len - 2 + 253) / 254;
     const int n_items = a.n_frames * nblk;
     const int n_pairs = (n_items + 1) / 2;
-    if (a.frame_len < kBlock || (a.row_stride & 1) || (a.frame_stride & 1) || (a.frame_len & 1)) return cudaErrorInvalidValue;
+    if (a.frame_len < kBlock || (!a.wire && (a.row_stride & 1)) || (a.frame_stride & 1) || (a.frame_len & 1)) return cudaErrorInvalidValue;
 
     PackArgs p{};
+    p.wire = a.wire;
+    p.wire_cols = a.wire_cols;
     p.stream = a.stream;
     p.row_stride = a.row_stride;
     p.row_len = a.row_len;
@@ -407,8 +457,10 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         ps.pair0 = p0;
         ks.pair0 = p0;
         dim3 pg((a.geom.row_chunks + 255) / 256, a.usable, np);
+        dim3 wg((a.geom.row_chunks + kWireChunks - 1) / kWireChunks, (a.usable + kWireCh - 1) / kWireCh, np);
         if (hook) hook(hook_ctx, 1, true, st);
-        pack_kernel<<<pg, 256, 0, st>>>(ps);
+        if (a.wire) pack_wire_kernel<<<wg, 256, 0, st>>>(ps);
+        else pack_kernel<<<pg, 256, 0, st>>>(ps);
         if (hook) hook(hook_ctx, 1, false, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

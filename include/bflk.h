@@ -105,6 +105,13 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
  * (src/fpga/receiver.h:24-30).  The conversion of Pipeline::receive_exposure (serpentine un-flip, / 2^23,
  * src/fpga/pipeline.cpp:260-297) runs on the device and feeds the power map without a host round trip. */
 int bflk_power_map_i32(bflk_handle *h, const int32_t *frames, float *power_out);
+/* A batch from the wire format: frames[T][C] int32 (T time samples, every sensor of the message in wire order), frame b
+ * uses rows [b*N, b*N + H + N + 1).  One fused pass turns the wire samples into the kernel's staged layout (un-flip
+ * folded into the column index, / 2^23, transpose, pair-interleave): no float copy of the stream exists, and the maps
+ * are bit-identical to bflk_power_map_batch on the converted stream.  power_out[B][count]. */
+int bflk_power_map_batch_i32(bflk_handle *h, const int32_t *frames, int64_t n_samples, int32_t n_frames, float *power_out);
+int bflk_power_map_batch_i32_dev(bflk_handle *h, const int32_t *frames_dev, int64_t n_samples, int32_t n_frames,
+                                 float *power_dev, void *cuda_stream);
 /* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream);

@@ -508,6 +508,32 @@ def test_power_map_from_wire_samples(bf, oracle):
     assert np.array_equal(p, w.update(exposure))           # same bits as feeding the converted floats
 
 
+@pytest.mark.parametrize("kernel", [0, 2, 3, 1])
+def test_batch_from_wire_samples_equals_float_path(bf, oracle, kernel):
+    """f1 fused: a batch of wire frames [T][C] int32 goes through ONE pass (un-flip, / 2^23, transpose, pair-interleave) into
+    the staged rows of the tiled kernel -- bit-identical to the float path on oracle-converted samples, for every kernel
+    (the non-tiled ones convert with the ingest kernel first), with a channel mask and a ragged direction range."""
+    from bflk import synth
+    c = cases.CONFIGS["cfg2"]
+    B = 5
+    w = bf.MIMOWorker(cases.origins(c["nx"], c["ny"]), 24, 20, c["fov"])
+    w.set_kernel(kernel)
+    T = (B - 1) * 256 + 1024
+    stream = _synth_window(bf, c, n_samples=T)
+    wire = synth.to_wire_i32(stream)                        # [T][C]
+    exposure = oracle.ingest(wire)                          # the reference's conversion (pipeline.cpp:260-297): [C][T]
+    ref = w.power_map_batch(exposure, B)
+    got = w.power_map_batch_i32(wire, B)
+    assert np.array_equal(got, ref)
+    off, fr = w.tables()
+    po = oracle.mimo_update(np.ascontiguousarray(exposure[:, 512:512 + 1024]), off, fr)
+    assert rel_err(got[2], po) <= POWER_RTOL
+    mask = np.r_[np.arange(3, 200, 2), np.arange(201, 256)].astype(np.int32)
+    w.set_channel_mask(mask)
+    w.set_direction_range(37, 301)
+    assert np.array_equal(w.power_map_batch_i32(wire, B), w.power_map_batch(exposure, B))
+
+
 def test_chunked_host_batch_equals_small_batches(bf):
     """Host-buffer batches above ~96 MiB are copied and computed in overlapping chunks: same bits as separate calls."""
     from bflk import synth
