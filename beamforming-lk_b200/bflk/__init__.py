@@ -32,7 +32,7 @@ SYMBOLS = [
     "bflk_power_map_batch", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
-    "bflk_heatmap", "bflk_calibrate", "bflk_ingest_i32",
+    "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
     "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded",
     "bflk_group_create", "bflk_group_destroy", "bflk_group_size", "bflk_group_handle", "bflk_group_last_error",
@@ -45,6 +45,12 @@ class Config(C.Structure):
     _fields_ = [("n_channels", C.c_int32), ("frame_len", C.c_int32), ("history", C.c_int32),
                 ("window_len", C.c_int32), ("sample_rate", C.c_double), ("propagation_speed", C.c_double),
                 ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Target(C.Structure):
+    """struct bflk_target (Target of src/dsp/worker.h:32-61 for a peak of the MIMO map)."""
+    _fields_ = [("theta", C.c_double), ("phi", C.c_double), ("power", C.c_float), ("probability", C.c_float),
+                ("direction", C.c_int32), ("row", C.c_int32), ("col", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BflkError(RuntimeError):
@@ -104,6 +110,10 @@ def load_library():
     L.bflk_monopulse.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     L.bflk_set_fir.argtypes = [vp, vp, i32, i32]
     L.bflk_heatmap.argtypes = [vp, vp, i32, vp, C.POINTER(i32), C.POINTER(f32)]
+    L.bflk_pin_host.argtypes = [vp, C.c_size_t]
+    L.bflk_unpin_host.argtypes = [vp]
+    L.bflk_resize_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.bflk_targets.argtypes = [vp, vp, i32, f32, vp, C.POINTER(i32)]
     L.bflk_calibrate.argtypes = [vp, vp, i32, f32, vp, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
     L.bflk_ingest_i32.argtypes = [vp, vp, i32, i32, vp]
     L.bflk_comm_unique_id.argtypes = [vp]
@@ -404,6 +414,23 @@ class Beamformer:
         arg, mx = C.c_int32(), C.c_float()
         self._check(self._L.bflk_heatmap(self._h, _ptr(power), power.shape[0], _ptr(heat), C.byref(arg), C.byref(mx)))
         return heat, arg.value, mx.value
+
+    def resize_u8(self, image, out_rows, out_cols):
+        """cv::resize(image, (out_cols, out_rows), INTER_LINEAR) of an 8-bit map, bit-identical to OpenCV."""
+        image = _np(image, np.uint8)
+        out = np.zeros((out_rows, out_cols), np.uint8)
+        self._check(self._L.bflk_resize_u8(self._h, _ptr(image), image.shape[0], image.shape[1], out_rows, out_cols, _ptr(out)))
+        return out
+
+    def targets(self, power=None, max_targets=8, min_rel_power=0.5):
+        """Peaks of the map as Targets: list of dicts; power=None uses the map the last single-frame power_map left on the device."""
+        arr = (Target * max_targets)()
+        n = C.c_int32()
+        if power is not None:
+            power = _np(power, np.float32).ravel()
+        self._check(self._L.bflk_targets(self._h, _ptr(power) if power is not None else None, max_targets, float(min_rel_power), arr, C.byref(n)))
+        return [dict(theta=t.theta, phi=t.phi, power=t.power, probability=t.probability, direction=t.direction, row=t.row, col=t.col)
+                for t in arr[:n.value]]
 
     def calibrate(self, signals, reference_power_level=1e-5):
         signals = _np(signals, np.float32)

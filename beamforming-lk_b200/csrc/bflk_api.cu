@@ -93,7 +93,7 @@ int bflk_destroy(bflk_handle *h) {
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release(); h->p_stage.release();
-    h->d_wire.release(); h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
+    h->d_bytes.release(); h->d_wire.release(); h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
     if (h->caller_event) cudaEventDestroy(h->caller_event);
     delete h;
     return BFLK_OK;
@@ -810,6 +810,7 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
                                      cudaMemcpyDeviceToHost, h->stream));
     }
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_map_on_device = n_frames == 1;   // d_power[0 .. count) is the map: bflk_targets(NULL) / bflk_heatmap(NULL) use it
     return BFLK_OK;
 }
 
@@ -1139,15 +1140,26 @@ int bflk_monopulse(bflk_handle *h, double *theta, const double *phi, int32_t n_p
 }
 
 // ---- neighbours of the path ------------------------------------------------------------------------------------
+int bflk_pin_host(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return BFLK_ERR_INVALID;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? BFLK_OK : BFLK_ERR_CUDA;
+}
+
+int bflk_unpin_host(void *ptr) {
+    if (!ptr) return BFLK_ERR_INVALID;
+    return cudaHostUnregister(ptr) == cudaSuccess ? BFLK_OK : BFLK_ERR_CUDA;
+}
+
 int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv) {
     if (!h) return BFLK_ERR_INVALID;
-    if (!power || n <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_heatmap: null / empty map");
+    if (n <= 0 || (!power && !(h->last_map_on_device && n == h->dir_count)))
+        return h->fail(BFLK_ERR_INVALID, "bflk_heatmap: null / empty map (and no map of that size left on the device)");
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
     BFLK_CUDA(h, h->d_power.reserve(n));
     BFLK_CUDA(h, h->d_misc.reserve(4 + (n + 3) / 4));
     BFLK_CUDA(h, h->p_misc.reserve(4));
     uint8_t *d_heat = reinterpret_cast<uint8_t *>(h->d_misc.p + 4);
-    BFLK_CUDA(h, cudaMemcpyAsync(h->d_power.p, power, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (power) BFLK_CUDA(h, cudaMemcpyAsync(h->d_power.p, power, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     BFLK_CUDA(h, launch_heatmap(h->d_power.p, n, d_heat, h->d_misc.p, reinterpret_cast<float *>(h->d_misc.p + 1), h->stream));
     h->launches++;
     BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1155,6 +1167,79 @@ int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, i
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     if (argmax) *argmax = h->p_misc.p[0];
     if (maxv) std::memcpy(maxv, &h->p_misc.p[1], sizeof(float));
+    return BFLK_OK;
+}
+
+// cv::resize coefficient tables for one axis (INTER_LINEAR, 8-bit: shorts scaled by 2048).  The horizontal axis clamps
+// the fraction to 0 where the two taps would leave the image, the vertical one keeps it and clips the row (as OpenCV does).
+static void resize_axis(int isz, int osz, bool clamp, int32_t *ofs, int32_t *coef) {
+    const double inv = (double)osz / (double)isz, scale = 1.0 / inv;
+    for (int d = 0; d < osz; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int sx = (int)std::floor(f);
+        f -= (float)sx;
+        if (clamp) {
+            if (sx < 0) { f = 0.f; sx = 0; }
+            if (sx >= isz - 1) { f = 0.f; sx = isz - 1; }
+        }
+        const int a0 = (int)std::lrintf((1.f - f) * 2048.f), a1 = (int)std::lrintf(f * 2048.f);
+        ofs[d] = sx;
+        coef[d] = (a0 & 0xffff) | (a1 << 16);
+    }
+}
+
+int bflk_resize_u8(bflk_handle *h, const uint8_t *src, int32_t rows, int32_t cols, int32_t out_rows, int32_t out_cols, uint8_t *dst) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!src || !dst || rows <= 0 || cols <= 0 || out_rows <= 0 || out_cols <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_resize_u8: null / empty image");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t n_in = (size_t)rows * cols, n_out = (size_t)out_rows * out_cols, n_tab = 2 * (size_t)(out_rows + out_cols);
+    BFLK_CUDA(h, h->d_bytes.reserve(n_in + n_out + 16));
+    BFLK_CUDA(h, h->d_misc.reserve(n_tab));
+    std::vector<int32_t> tab(n_tab);
+    resize_axis(cols, out_cols, true, tab.data(), tab.data() + out_cols);
+    resize_axis(rows, out_rows, false, tab.data() + 2 * out_cols, tab.data() + 2 * out_cols + out_rows);
+    uint8_t *d_src = h->d_bytes.p, *d_dst = h->d_bytes.p + ((n_in + 15) & ~(size_t)15);
+    BFLK_CUDA(h, cudaMemcpyAsync(h->d_misc.p, tab.data(), n_tab * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, cudaMemcpyAsync(d_src, src, n_in, cudaMemcpyHostToDevice, h->stream));
+    BFLK_CUDA(h, launch_resize_u8(d_src, rows, cols, d_dst, out_rows, out_cols, h->d_misc.p, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(dst, d_dst, n_out, cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BFLK_OK;
+}
+
+int bflk_targets(bflk_handle *h, const float *power, int32_t max_targets, float min_rel_power, bflk_target *out, int32_t *n_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!out || !n_out || max_targets <= 0 || max_targets > 256) return h->fail(BFLK_ERR_INVALID, "bflk_targets: need 1..256 output slots");
+    if (!h->have_grid || h->rows <= 0 || h->cols <= 0 || h->dir_first != 0 || h->dir_count != h->n_dir)
+        return h->fail(BFLK_ERR_STATE, "bflk_targets: needs a rows x cols grid (bflk_set_grid_fov) and the whole map on this handle");
+    if (!power && !h->last_map_on_device) return h->fail(BFLK_ERR_STATE, "bflk_targets: no map given and none left on the device by bflk_power_map");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int D = h->n_dir;
+    BFLK_CUDA(h, h->d_power.reserve(D));
+    BFLK_CUDA(h, h->d_bytes.reserve(D));
+    BFLK_CUDA(h, h->d_misc.reserve(3 * (size_t)max_targets + 1));
+    BFLK_CUDA(h, h->p_misc.reserve(3 * (size_t)max_targets + 1));
+    if (power) BFLK_CUDA(h, cudaMemcpyAsync(h->d_power.p, power, D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int32_t *d_index = h->d_misc.p, *d_n = h->d_misc.p + 3 * max_targets;
+    float *d_pw = reinterpret_cast<float *>(h->d_misc.p + max_targets), *d_prob = reinterpret_cast<float *>(h->d_misc.p + 2 * max_targets);
+    BFLK_CUDA(h, launch_map_targets(h->d_power.p, h->rows, h->cols, max_targets, min_rel_power, h->d_bytes.p, d_index, d_pw, d_prob, d_n, h->stream));
+    h->launches++;
+    BFLK_CUDA(h, cudaMemcpyAsync(h->p_misc.p, h->d_misc.p, (3 * (size_t)max_targets + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int n = h->p_misc.p[3 * max_targets];
+    for (int i = 0; i < n; i++) {
+        bflk_target &t = out[i];
+        t.direction = h->p_misc.p[i];
+        t.row = t.direction / h->cols;
+        t.col = t.direction % h->cols;
+        t.theta = h->theta[t.direction];
+        t.phi = h->phi[t.direction];
+        std::memcpy(&t.power, &h->p_misc.p[max_targets + i], sizeof(float));
+        std::memcpy(&t.probability, &h->p_misc.p[2 * max_targets + i], sizeof(float));
+        t.reserved = 0;
+    }
+    *n_out = n;
     return BFLK_OK;
 }
 

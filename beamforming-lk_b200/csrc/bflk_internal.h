@@ -200,6 +200,8 @@ struct bflk_handle {
     const float *resident_window = nullptr;   // d_resident.p, or a caller-owned device pointer (bflk_set_window_dev)
     const int32_t *wire_src = nullptr;        // set for the duration of a wire-format call: power_map_dev packs from it
     bflk::DevBuf<int32_t> d_wire;
+    bflk::DevBuf<uint8_t> d_bytes;            // heat-map / resize / peak-candidate scratch
+    bool last_map_on_device = false;          // d_power holds the [count] map of the last single-frame call
     bflk::DevBuf<float> d_resident;
     bflk::DevBuf<float> d_miso_out;           // [flag | audio | power]: one D2H copy per call
     bflk::DevBuf<float> d_miso_partial;
@@ -372,6 +374,9 @@ cudaError_t launch_heatmap(const float *d_power, int n, uint8_t *d_heat, int32_t
 cudaError_t launch_channel_power(const float *d_signals, int n_ch, int W, float *d_power, cudaStream_t st);
 cudaError_t launch_ingest(const int32_t *d_frames, int n, int n_sensors, float *d_exposure, cudaStream_t st);
 cudaError_t launch_ffma2_peak(float *d_out, int n_blocks, int iters, cudaStream_t st);
+cudaError_t launch_resize_u8(const uint8_t *d_src, int ih, int iw, uint8_t *d_dst, int oh, int ow, const int32_t *d_tab, cudaStream_t st);
+cudaError_t launch_map_targets(const float *d_power, int rows, int cols, int max_targets, float min_rel, uint8_t *d_cand,
+                               int32_t *d_index, float *d_pw, float *d_prob, int32_t *d_n, cudaStream_t st);
 
 // ---- bflk_api.cu internals used by multi.cu ---------------------------------------------------------------
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold n_samples valid samples

@@ -21,6 +21,8 @@
  *   bflk_miso*                      Particle::steer + Particle::das + Particle::beam
  *                                   (src/dsp/particle.cpp:37-103) as used by MISOWorker::update (miso.cpp:39-46)
  *   bflk_heatmap                    MIMOWorker::populateHeatmap (src/dsp/mimo.cpp:61-95)
+ *   bflk_resize_u8                  cv::resize(..., INTER_LINEAR) in AWProcessingUnit::draw (aw_processing_unit.cpp:245-259)
+ *   bflk_targets                    Worker::tracking / getTargets (src/dsp/worker.h:32-61,136-142) for the MIMO map
  *   bflk_calibrate                  AWProcessingUnit::calibrate mask (aw_processing_unit.cpp:126-200)
  *   bflk_ingest_i32, bflk_power_map_i32   Pipeline::receive_exposure conversion (src/fpga/pipeline.cpp:260-297)
  *   bflk_comm_*, bflk_shard_plan, bflk_power_map_batch_sharded*, bflk_group_*   (no reference counterpart: the reference
@@ -223,8 +225,34 @@ int bflk_monopulse(bflk_handle *h, double *theta, const double *phi, int32_t n_p
                    double *q, double *gradient, double *error);
 
 /* ---- neighbours of the path ------------------------------------------------------------------------ */
-/* populateHeatmap: heat[count] = uchar(clip(255 * p / max)), argmax / max of the map. */
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so the H2D / D2H copies of the host-buffer entry points run at
+ * full PCIe speed and asynchronously; the Worker adapter pins its snapshot buffer once. */
+int bflk_pin_host(void *ptr, size_t bytes);
+int bflk_unpin_host(void *ptr);
+/* populateHeatmap: heat[count] = uchar(clip(255 * p / max)), argmax / max of the map.  power == NULL: the map the last
+ * bflk_power_map call left on the device (n must equal its size). */
 int bflk_heatmap(bflk_handle *h, const float *power, int32_t n, uint8_t *heat, int32_t *argmax, float *maxv);
+/* cv::resize(compact, normal, normal.size(), 0, 0, cv::INTER_LINEAR) of the 8-bit heat-map (AWProcessingUnit::draw,
+ * src/aw_processing_unit/aw_processing_unit.cpp:252): src[rows][cols] -> dst[out_rows][out_cols], bit-identical to
+ * OpenCV's fixed-point 8-bit bilinear path. */
+int bflk_resize_u8(bflk_handle *h, const uint8_t *src, int32_t rows, int32_t cols, int32_t out_rows, int32_t out_cols,
+                   uint8_t *dst);
+/* Peaks of the power map as Targets (struct Target, src/dsp/worker.h:32-61 -- what TargetHandler polls through
+ * AWProcessingUnit::targets(), src/target_handler/target_handler.cpp:29-36).  The reference's MIMO worker never fills
+ * Worker::tracking; this defines it: a grid direction is a target when it is the maximum of its 3x3 neighbourhood
+ * (ties: lowest index) and carries at least min_rel_power of the map's maximum; strongest first.  power = the map
+ * value; probability = 1 / gradientError as the gradient tracker reports it (src/dsp/gradient_ascend.cpp:62-76,406),
+ * with the four grid neighbours in place of the four quadrant beams.  power == NULL: the map the last bflk_power_map
+ * call left on the device (no upload).  Needs a bflk_set_grid_fov grid and the whole map on this handle. */
+typedef struct bflk_target {
+    double theta, phi;      /* Spherical direction of the grid cell (bflk_get_grid) */
+    float power;
+    float probability;
+    int32_t direction;      /* r * cols + c */
+    int32_t row, col;
+    int32_t reserved;
+} bflk_target;
+int bflk_targets(bflk_handle *h, const float *power, int32_t max_targets, float min_rel_power, bflk_target *out, int32_t *n_out);
 /* calibrate(): signals[64][W] of one array -> index[<=64], correction[<=64]; *usable = count. */
 int bflk_calibrate(bflk_handle *h, const float *signals, int32_t window_len, float reference_power_level,
                    int32_t *index, float *correction, int32_t *usable, float *median, float *mean);

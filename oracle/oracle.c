@@ -318,3 +318,96 @@ void orc_mimo_update_fir(const float *window, int C, int W, int n, const int *in
     }
     free(out);
 }
+
+/* ---- f3: the steps after the map: bilinear resize of the heat-map and peak -> Target ------------------------------ */
+/* cv::resize(compact, normal, normal.size(), 0, 0, cv::INTER_LINEAR) on CV_8UC1 (src/aw_processing_unit/
+ * aw_processing_unit.cpp:252).  OpenCV is a third-party dependency absent from /root/reference (libopencv-dev 4.5.4 in
+ * the reference's Dockerfile); its 8-bit INTER_LINEAR path is fixed point: coefficients cvRound(c * 2048) as short,
+ * horizontal pass in int, vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16), then (v + 2) >> 2.
+ * Horizontal coordinates clamp the fraction to 0 at the borders, vertical ones keep it and clip the row index.
+ * Pinned: tests/golden/resize.npz holds cv2.resize outputs (opencv-python 4.13, generated by make_golden.py). */
+static void resize_coeffs(int isz, int osz, int clamp, int *ofs, short *a0, short *a1) {
+    const double inv = (double)osz / (double)isz, scale = 1.0 / inv;
+    for (int d = 0; d < osz; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int sx = (int)floorf(f);
+        f -= (float)sx;
+        if (clamp) {
+            if (sx < 0) { f = 0.f; sx = 0; }
+            if (sx >= isz - 1) { f = 0.f; sx = isz - 1; }
+        }
+        ofs[d] = sx;
+        a0[d] = (short)lrintf((1.f - f) * 2048.f);
+        a1[d] = (short)lrintf(f * 2048.f);
+    }
+}
+
+void orc_resize_linear_u8(const uint8_t *src, int ih, int iw, uint8_t *dst, int oh, int ow) {
+    int *xo = (int *)malloc(sizeof(int) * ow), *yo = (int *)malloc(sizeof(int) * oh);
+    short *xa0 = (short *)malloc(2 * ow), *xa1 = (short *)malloc(2 * ow), *ya0 = (short *)malloc(2 * oh), *ya1 = (short *)malloc(2 * oh);
+    resize_coeffs(iw, ow, 1, xo, xa0, xa1);
+    resize_coeffs(ih, oh, 0, yo, ya0, ya1);
+    for (int y = 0; y < oh; y++) {
+        int y0 = yo[y] < 0 ? 0 : (yo[y] > ih - 1 ? ih - 1 : yo[y]);
+        int y1 = yo[y] + 1 < 0 ? 0 : (yo[y] + 1 > ih - 1 ? ih - 1 : yo[y] + 1);
+        for (int x = 0; x < ow; x++) {
+            int x0 = xo[x], x1 = x0 + 1 > iw - 1 ? iw - 1 : x0 + 1;
+            int S0 = src[y0 * iw + x0] * xa0[x] + src[y0 * iw + x1] * xa1[x];
+            int S1 = src[y1 * iw + x0] * xa0[x] + src[y1 * iw + x1] * xa1[x];
+            int v = ((ya0[y] * (S0 >> 4)) >> 16) + ((ya1[y] * (S1 >> 4)) >> 16);
+            v = (v + 2) >> 2;
+            dst[y * ow + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(xo); free(yo); free(xa0); free(xa1); free(ya0); free(ya1);
+}
+
+/* Peaks of the MIMO map as Targets (a14: src/dsp/worker.h:32-61; the gradient worker is the reference's only producer,
+ * src/dsp/gradient_ascend.cpp:399-408).  NEW behaviour, defined here and mirrored by the library: a grid direction is a
+ * target when it is the maximum of its 3x3 neighbourhood (ties: lowest index) and carries at least min_rel of the map's
+ * maximum; targets come in order of decreasing power (ties: index).  power = the map value (the tracker reports the mean
+ * beam power around its direction); probability = 1 / gradientError like the tracker's, with gradientError formed from
+ * the four grid neighbours instead of the four quadrant beams (gradient_ascend.cpp:62-76): (|right - left| + |down - up|)
+ * / (left + right + up + down), a missing neighbour at the border replaced by the direction itself. */
+int orc_map_targets(const float *power, int rows, int cols, int max_targets, float min_rel, int *index, float *pw, float *prob) {
+    const int D = rows * cols;
+    float maxV = 0.0f;
+    for (int i = 0; i < D; i++) if (power[i] > maxV) maxV = power[i];
+    const float thr = min_rel * maxV;
+    unsigned char *taken = (unsigned char *)calloc(D, 1);
+    int n = 0;
+    while (n < max_targets) {
+        int best = -1;
+        for (int i = 0; i < D; i++) {
+            if (taken[i]) continue;
+            const float p = power[i];
+            if (!(p >= thr) || !(p > 0.0f)) continue;
+            const int r = i / cols, c = i % cols;
+            int is_max = 1;
+            for (int dr = -1; dr <= 1 && is_max; dr++)
+                for (int dc = -1; dc <= 1; dc++) {
+                    const int rr = r + dr, cc = c + dc;
+                    if ((dr == 0 && dc == 0) || rr < 0 || rr >= rows || cc < 0 || cc >= cols) continue;
+                    const int j = rr * cols + cc;
+                    if (power[j] > p || (power[j] == p && j < i)) { is_max = 0; break; }
+                }
+            if (!is_max) continue;
+            if (best < 0 || p > power[best]) best = i;      /* index order breaks ties towards the lower index */
+        }
+        if (best < 0) break;
+        taken[best] = 1;
+        const int r = best / cols, c = best % cols;
+        const float p = power[best];
+        const double ql = c > 0 ? power[best - 1] : p, qr = c < cols - 1 ? power[best + 1] : p;
+        const double qu = r > 0 ? power[best - cols] : p, qd = r < rows - 1 ? power[best + cols] : p;
+        const double err = (fabs(qr - ql) + fabs(qd - qu)) / (((ql + qr) + qu) + qd);
+        double pr = 1.0 / err;
+        if (!(pr < 3.4028234663852886e38)) pr = 3.4028234663852886e38;
+        index[n] = best;
+        pw[n] = p;
+        prob[n] = (float)pr;
+        n++;
+    }
+    free(taken);
+    return n;
+}

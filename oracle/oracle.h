@@ -100,4 +100,8 @@ void orc_mimo_update_fir(const float *window, int C, int W, int n, const int *in
 #ifdef __cplusplus
 }
 #endif
+/* f3: cv::resize INTER_LINEAR on 8-bit maps (aw_processing_unit.cpp:252) and map peaks as Targets (worker.h:32-61) */
+void orc_resize_linear_u8(const uint8_t *src, int ih, int iw, uint8_t *dst, int oh, int ow);
+int orc_map_targets(const float *power, int rows, int cols, int max_targets, float min_rel, int *index, float *pw, float *prob);
+
 #endif

@@ -66,6 +66,10 @@ def lib():
         L.orc_calibrate.argtypes = [_f32p, C.c_int, C.c_float, _i32p, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_calibrate.restype = C.c_int
         L.orc_ingest.argtypes = [_i32p, C.c_int, C.c_int, _f32p]
+        L.orc_resize_linear_u8.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+        L.orc_resize_linear_u8.restype = None
+        L.orc_map_targets.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_float, _i32p, _f32p, _f32p]
+        L.orc_map_targets.restype = C.c_int
         _lib = L
     return _lib
 
@@ -311,3 +315,22 @@ def mimo_update_fir(window, offsets, fractions, coeffs, index=None, n=N_SAMPLES)
     lib().orc_mimo_update_fir(window, Cn, W, n, index, len(index), np.ascontiguousarray(offsets, np.int32),
                               np.ascontiguousarray(fractions, np.float32), D, coeffs, coeffs.shape[0], coeffs.shape[1], power)
     return power
+
+
+# ---- after the map: heat-map resize, peaks as Targets -----------------------------------------------------------
+def resize_linear_u8(src, out_rows, out_cols):
+    """cv::resize(..., INTER_LINEAR) on an 8-bit map (aw_processing_unit.cpp:252), fixed-point restatement."""
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((out_rows, out_cols), np.uint8)
+    lib().orc_resize_linear_u8(src, src.shape[0], src.shape[1], dst, out_rows, out_cols)
+    return dst
+
+
+def map_targets(power, rows, cols, max_targets=8, min_rel=0.5):
+    """Peaks of a rows x cols power map: (index [n], power [n], probability [n])."""
+    power = np.ascontiguousarray(power, np.float32).ravel()
+    idx = np.zeros(max_targets, np.int32)
+    pw = np.zeros(max_targets, np.float32)
+    pr = np.zeros(max_targets, np.float32)
+    n = lib().orc_map_targets(power, rows, cols, max_targets, min_rel, idx, pw, pr)
+    return idx[:n].copy(), pw[:n].copy(), pr[:n].copy()

@@ -95,7 +95,24 @@ def main():
     np.savez_compressed(os.path.join(HERE, "fir.npz"), coeffs=coeffs, ref_power=fir_ref_power, power=fir_power,
                         kat_signal=sig, kat_fraction=fracs, kat_out=outs)
     print("FIR: oracle vs compiled reference power max rel diff", np.max(np.abs(fir_ref_power - fir_power) / fir_power))
-    for f in ("tables.npz", "snapshot.npz", "fir.npz"):
+    # ---- H: cv::resize(INTER_LINEAR) on 8-bit maps, from the real OpenCV (opencv-python; the reference links libopencv) ----
+    import cv2
+    rng = np.random.default_rng(9)
+    res = {"cv2_version": np.array(cv2.__version__)}
+    heat16 = heat.reshape(16, 16)
+    big = cv2.resize(heat16, (1024, 1024), interpolation=cv2.INTER_LINEAR)       # AWProcessingUnit::draw: compact -> 1024 x 1024
+    res["heat16"], res["heat16_to_1024_sha"] = heat16, np.frombuffer(bytes.fromhex(sha(big)), np.uint8)
+    res["heat16_to_1024_rows"] = big[::97]
+    for k, (ih, iw, oh, ow) in enumerate(((16, 16, 37, 53), (100, 100, 1024, 1024), (9, 11, 64, 48), (256, 256, 1024, 1024), (100, 100, 50, 60), (1, 1, 8, 8))):
+        src = rng.integers(0, 256, (ih, iw), dtype=np.uint8)
+        out = cv2.resize(src, (ow, oh), interpolation=cv2.INTER_LINEAR)
+        res[f"case{k}_src"] = src
+        res[f"case{k}_shape"] = np.array([oh, ow])
+        res[f"case{k}_sha"] = np.frombuffer(bytes.fromhex(sha(out)), np.uint8)
+        if out.size <= 4096:
+            res[f"case{k}_out"] = out
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **res)
+    for f in ("tables.npz", "snapshot.npz", "fir.npz", "resize.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

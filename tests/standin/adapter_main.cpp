@@ -41,25 +41,40 @@ int main(int argc, char **argv) {
         pipeline.streams.forward();
     }
     {
-        CudaMIMOWorker mimo(&pipeline, antenna, &running, rows, cols, fov);
-        CudaMISOWorker miso(&pipeline, antenna, &running, fov);
-        mimo.update_once();
+        // created and destroyed the way AWProcessingUnit does: new in start() (aw_processing_unit.cpp:67-95), delete through
+        // Worker* in the destructor (aw_processing_unit.cpp:51-53) -- ~Worker is not virtual
+        CudaMIMOWorker *mimo = new CudaMIMOWorker(&pipeline, antenna, &running, rows, cols, fov);
+        CudaMISOWorker *miso = new CudaMISOWorker(&pipeline, antenna, &running, fov);
+        std::vector<Worker *> workers = {mimo, miso};
+        mimo->update_once();
         cv::Mat heat(rows, cols);
-        mimo.draw(&heat);
-        printf("type %d %d\n", (int)mimo.get_type(), (int)miso.get_type());
+        mimo->draw(&heat);
+        printf("type %d %d\n", (int)mimo->get_type(), (int)miso->get_type());
         printf("power");
-        for (float p : mimo.power()) printf(" %.9g", p);
+        for (float p : mimo->power()) printf(" %.9g", p);
         printf("\nheat");
         for (uchar h : heat.store) printf(" %d", (int)h);
         printf("\n");
-        miso.steer(Spherical(theta, phi));
-        miso.update_once();
-        printf("beam %.9g\naudio", miso.beam_power());
-        for (int i = 0; i < N_SAMPLES; i++) printf(" %.9g", miso.audio()[i]);
+        // AWProcessingUnit::targets() = workers[0]->getTargets() (aw_processing_unit.cpp:267-269), polled by TargetHandler
+        const std::vector<Target> first = workers[0]->getTargets();
+        printf("targets");
+        for (const Target &t : first) printf(" %.17g %.17g %.9g %.9g", t.direction.theta, t.direction.phi, t.power, t.probability);
+        printf("\n");
+        mimo->update_once();
+        const std::vector<Target> second = workers[0]->getTargets();
+        int kept = second.size() == first.size();
+        for (size_t i = 0; kept && i < second.size(); i++) kept = second[i] == first[i] && second[i].start == first[i].start;
+        printf("start_kept %d\n", kept);
+        miso->steer(Spherical(theta, phi));
+        miso->update_once();
+        printf("beam %.9g\naudio", miso->beam_power());
+        for (int i = 0; i < N_SAMPLES; i++) printf(" %.9g", miso->audio()[i]);
         printf("\n");
         pipeline.release_barrier();  // one live frame through both Worker::loop() threads
         std::this_thread::sleep_for(std::chrono::milliseconds(50));
         pipeline.stop();             // AWProcessingUnit::~AWProcessingUnit disconnects before deleting workers
+        for (Worker *job : workers) delete job;
+        printf("deleted_through_base 1\n");
     }
     pipeline.stop();
     return 0;

@@ -6,6 +6,8 @@
 // stand-ins only reproduce names, member order and call contracts.
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -85,6 +87,19 @@ public:
     void stop() { running = false; cv_.notify_all(); }
 };
 
+// src/dsp/worker.h:32-61
+struct Target {
+    Spherical direction;
+    float power;
+    float probability;
+    std::chrono::time_point<std::chrono::high_resolution_clock> start;
+    bool operator==(const Target &other) const {
+        return fabs(direction.phi - other.direction.phi) < 1e-2 && fabs(direction.theta - other.direction.theta) < 1e-2;
+    }
+    Target(Spherical direction, float power, float probability, std::chrono::time_point<std::chrono::high_resolution_clock> start)
+        : direction(direction), power(power), probability(probability), start(start) {}
+};
+
 enum worker_t { GENERIC, PSO, MIMO, MISO, SOUND, GRADIENT };
 
 class Worker {
@@ -96,9 +111,14 @@ public:
     Worker(Pipeline *pipeline, Antenna &antenna, bool *running) : running(running), looping(true), pipeline(pipeline), antenna(antenna) {
         streams = pipeline->getStreams();
     }
-    virtual ~Worker() {
+    ~Worker() {   // NOT virtual, like the reference (src/dsp/worker.h:111-114): AWProcessingUnit deletes through Worker*
         looping = false;
         thread_loop.join();
+    }
+    std::vector<Target> getTargets() const {   // worker.h:136-142 (called without the lock by TargetHandler)
+        std::vector<Target> r_targets;
+        for (size_t i = 0; i < tracking.size(); ++i) r_targets.insert(r_targets.end(), tracking[i]);
+        return r_targets;
     }
     virtual worker_t get_type() { return worker_t::GENERIC; }
     void draw(cv::Mat *heatmap) {
@@ -112,6 +132,7 @@ protected:
     Spherical direction;
     Streams *streams;
     Antenna &antenna;
+    std::vector<Target> tracking;
     virtual void update() {}
     virtual void reset() {}
     virtual void populateHeatmap(cv::Mat *) {}

@@ -34,6 +34,7 @@ def test_adapter_compiles_against_worker_interface(tmp_path):
         assert r.returncode == 0
         assert "no CPU fallback" in r.stderr or "no CUDA device" in r.stderr
         assert "power 0 0 0" in r.stdout          # powerdB untouched
+        assert "deleted_through_base 1" in r.stdout
 
 
 @pytest.mark.gpu
@@ -55,3 +56,13 @@ def test_adapter_matches_golden_on_gpu(tmp_path, golden):
     audio = np.array(out["audio"].split(), np.float32)
     assert np.array_equal(audio, g["miso_audio"][0])          # das(): bit-exact (%.9g round-trips float32)
     assert abs(float(out["beam"]) - g["miso_beam"][0]) <= 1e-4 * g["miso_beam"][0]
+    # Worker::tracking as TargetHandler reads it (AWProcessingUnit::targets): the map's peaks, per the oracle's definition
+    from oracle import oracle as O
+    idx, pw, pr = O.map_targets(g["power"], 16, 16, 8, 0.5)
+    th_grid, ph_grid = O.mimo_grid(16, 16, 180.0)
+    t = np.array(out["targets"].split(), np.float64).reshape(-1, 4)
+    assert t.shape[0] == len(idx) >= 1
+    assert np.array_equal(t[:, 0], th_grid[idx]) and np.array_equal(t[:, 1], ph_grid[idx])
+    assert np.allclose(t[:, 2], pw, rtol=1e-4) and np.allclose(t[:, 3], pr, rtol=2e-3)
+    assert out["start_kept"] == "1"               # the same target on the next frame keeps its first-found time
+    assert out["deleted_through_base"] == "1"     # delete through Worker* (non-virtual ~Worker) shut down cleanly

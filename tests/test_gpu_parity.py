@@ -577,6 +577,45 @@ def test_caller_supplied_tables_and_errors(bf, oracle):
     assert e.value.code == -5
 
 
+def test_resize_and_targets_after_the_map(bf, oracle, golden):
+    """f3 / a14: the steps after the map on the device -- heat-map bilinear resize bit-identical to OpenCV (golden from cv2)
+    and the oracle, map peaks as Targets equal to the oracle's definition, also from the map left on the device."""
+    g, snap = golden["resize"], golden["snapshot"]
+    b = bf.Beamformer()
+    big = b.resize_u8(g["heat16"], 1024, 1024)
+    assert np.array_equal(sha(big), g["heat16_to_1024_sha"]) and np.array_equal(big[::97], g["heat16_to_1024_rows"])
+    k = 0
+    while f"case{k}_src" in g:
+        oh, ow = (int(v) for v in g[f"case{k}_shape"])
+        out = b.resize_u8(g[f"case{k}_src"], oh, ow)
+        assert np.array_equal(sha(out), g[f"case{k}_sha"])
+        assert np.array_equal(out, oracle.resize_linear_u8(g[f"case{k}_src"], oh, ow))
+        k += 1
+    assert k >= 5
+    for name in ("cfg1", "cfg3"):
+        c = cases.CONFIGS[name]
+        w = make(bf, c)
+        window = _synth_window(bf, c)
+        p = w.update(window)
+        for max_t, rel in ((8, 0.05), (1, 0.5), (32, 0.001)):
+            idx, pw, pr = oracle.map_targets(p, c["rows"], c["cols"], max_t, rel)
+            got = w.targets(max_targets=max_t, min_rel_power=rel)                      # the map left on the device
+            assert [t["direction"] for t in got] == idx.tolist()
+            assert np.array_equal(np.array([t["power"] for t in got], np.float32), pw)
+            assert np.array_equal(np.array([t["probability"] for t in got], np.float32), pr)
+            got2 = w.targets(p, max_targets=max_t, min_rel_power=rel)                  # the same map handed over
+            assert got2 == got
+        th, ph = w.grid()
+        t0 = w.targets(max_targets=1)[0]
+        assert t0["direction"] == int(np.argmax(p)) and t0["theta"] == th[t0["direction"]] and t0["phi"] == ph[t0["direction"]]
+        assert (t0["row"], t0["col"]) == divmod(t0["direction"], c["cols"])
+        # the strongest source of the synthetic scene after the high-pass is the 9 kHz boresight tone: theta ~ 0
+        assert t0["theta"] < np.deg2rad(8.0)
+    w.set_direction_range(0, 10)
+    with pytest.raises(bf.BflkError):
+        w.targets(max_targets=2)                                                       # needs the whole map
+
+
 def test_launch_counter(bf, golden):
     w = bf.MIMOWorker(cases.origins(1, 1), 16, 16, 180.0)
     n0 = w.launch_count()

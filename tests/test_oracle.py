@@ -304,3 +304,60 @@ def test_exposure_of_unpinned_eigen_order(oracle):
         # a delay is at most ~100 samples: one float ulp there is 7.6e-6; every alternative stays within a few ulps
         assert worst <= 4e-5
         assert share_off <= 2e-3                                 # offset flips only where a delay sits on an integer
+
+
+# ---- f3: heat-map resize pinned against OpenCV, map peaks as Targets ---------------------------------------------------
+def _resize_cases(g):
+    k = 0
+    while f"case{k}_src" in g:
+        yield g[f"case{k}_src"], int(g[f"case{k}_shape"][0]), int(g[f"case{k}_shape"][1]), g[f"case{k}_sha"], g.get(f"case{k}_out")
+        k += 1
+
+
+def test_resize_matches_opencv_golden(oracle, golden):
+    """cv::resize(..., INTER_LINEAR) on CV_8UC1 (aw_processing_unit.cpp:252): OpenCV is absent from /root/reference, the
+    golden outputs come from the real cv2.resize (tests/golden/make_golden.py); the fixed-point restatement is bit-exact."""
+    g = golden["resize"]
+    big = oracle.resize_linear_u8(g["heat16"], 1024, 1024)
+    assert np.array_equal(sha(big), g["heat16_to_1024_sha"]) and np.array_equal(big[::97], g["heat16_to_1024_rows"])
+    for src, oh, ow, want_sha, want in _resize_cases(g):
+        out = oracle.resize_linear_u8(src, oh, ow)
+        assert np.array_equal(sha(out), want_sha)
+        if want is not None:
+            assert np.array_equal(out, want)
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(3)
+    for _ in range(10):
+        ih, iw, oh, ow = (int(v) for v in rng.integers(1, 70, 4))
+        src = rng.integers(0, 256, (ih, iw), dtype=np.uint8)
+        assert np.array_equal(oracle.resize_linear_u8(src, oh, ow), cv2.resize(src, (ow, oh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_map_targets_definition(oracle, golden):
+    """Peaks of the map as Targets (new behaviour, see oracle.c): local maxima above a share of the peak, strongest first,
+    probability = 1 / gradientError from the four grid neighbours."""
+    g = golden["snapshot"]
+    idx, pw, pr = oracle.map_targets(g["power"], 16, 16, max_targets=8, min_rel=0.05)
+    assert idx[0] == int(np.argmax(g["power"])) and pw[0] == g["power"].max()
+    assert np.all(np.diff(pw) <= 0) and len(set(idx.tolist())) == len(idx)
+    m = g["power"].reshape(16, 16)
+    for i in idx:
+        r, c = divmod(int(i), 16)
+        assert m[r, c] == m[max(r - 1, 0):r + 2, max(c - 1, 0):c + 2].max() and m[r, c] >= 0.05 * m.max()
+    r, c = divmod(int(idx[0]), 16)
+    err = (abs(float(m[r, c + 1]) - float(m[r, c - 1])) + abs(float(m[r + 1, c]) - float(m[r - 1, c]))) / (float(m[r, c - 1]) + float(m[r, c + 1]) + float(m[r - 1, c]) + float(m[r + 1, c]))
+    assert np.isclose(pr[0], 1.0 / err, rtol=1e-6)
+    # a plateau yields ONE target (the lowest index), a flat neighbourhood an (almost) infinite probability
+    flat = np.zeros((6, 6), np.float32)
+    flat[2:4, 2:4] = 1.0
+    i2, p2, q2 = oracle.map_targets(flat, 6, 6, 4, 0.5)
+    assert i2.tolist() == [14] and p2[0] == 1.0
+    two = np.full((8, 8), 0.1, np.float32)
+    two[1, 1], two[6, 5] = 3.0, 2.0
+    i3, p3, _ = oracle.map_targets(two, 8, 8, 4, 0.5)
+    assert i3.tolist() == [9, 53] and p3.tolist() == [3.0, 2.0]
+    assert oracle.map_targets(two, 8, 8, 4, 0.9)[0].tolist() == [9]          # threshold relative to the peak
+    assert oracle.map_targets(two, 8, 8, 1, 0.1)[0].tolist() == [9]          # k limits the list
