@@ -27,7 +27,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_BCAST, KERNEL_TILED_FMA2 = 0, 
 SYMBOLS = [
     "bflk_default_config", "bflk_version", "bflk_create", "bflk_destroy", "bflk_last_error",
     "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
-    "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_direction_range", "bflk_get_n_directions",
+    "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_grid_shape", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
@@ -85,6 +85,7 @@ def load_library():
     L.bflk_set_channel_mask.argtypes = [vp, vp, i32]
     L.bflk_set_grid_fov.argtypes = [vp, i32, i32, f32]
     L.bflk_set_grid_tables.argtypes = [vp, vp, vp, i32]
+    L.bflk_set_grid_shape.argtypes = [vp, i32, i32]
     L.bflk_set_direction_range.argtypes = [vp, i32, i32]
     L.bflk_get_n_directions.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.bflk_get_grid.argtypes = [vp, vp, vp]
@@ -287,6 +288,10 @@ class Beamformer:
         offsets, fractions = _np(offsets, np.int32), _np(fractions, np.float32)
         assert offsets.shape == fractions.shape and offsets.shape[1] == self.n_channels
         self._check(self._L.bflk_set_grid_tables(self._h, _ptr(offsets), _ptr(fractions), offsets.shape[0]))
+
+    def set_grid_shape(self, rows, cols):
+        """Caller-supplied tables are a row-major rows x cols grid: lets the register-tiled kernels serve them."""
+        self._check(self._L.bflk_set_grid_shape(self._h, rows, cols))
 
     def set_direction_range(self, first, count):
         self._check(self._L.bflk_set_direction_range(self._h, first, count))

@@ -299,6 +299,18 @@ int bflk_set_grid_tables(bflk_handle *h, const int32_t *offsets, const float *fr
     return BFLK_OK;
 }
 
+int bflk_set_grid_shape(bflk_handle *h, int32_t rows, int32_t cols) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_set_grid_shape: set the tables first");
+    if (rows <= 0 || cols <= 0 || (int64_t)rows * cols != h->n_dir)
+        return h->fail(BFLK_ERR_INVALID, "bflk_set_grid_shape: %d x %d is not the %d directions of the tables", rows, cols, h->n_dir);
+    h->rows = rows;
+    h->cols = cols;
+    h->tiles_valid = false;
+    h->bcast_valid = false;
+    return BFLK_OK;
+}
+
 int bflk_set_direction_range(bflk_handle *h, int32_t first, int32_t count) {
     if (!h) return BFLK_ERR_INVALID;
     if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_set_direction_range: set the grid first");
@@ -452,11 +464,12 @@ int64_t min_stream_samples(const bflk_handle *h, int n_frames) {
 
 // Builds (once per grid / mask / range) the packed tables of the register-tiled kernel.  tiles_valid is set only after
 // the last step has succeeded, so a failed build is retried (and reported again) by the next call.
-int ensure_tiles(bflk_handle *h, int fast) {
-    if (h->tiles_valid && h->tiles_fast == fast) return BFLK_OK;
+int ensure_tiles(bflk_handle *h, int fast, int want_warps) {
+    if (h->tiles_valid && h->tiles_fast == fast && h->tiles_want_warps == want_warps) return BFLK_OK;
     if (h->caller_event) BFLK_CUDA(h, cudaEventSynchronize(h->caller_event));   // a queued kernel may still read the old tables
     h->tiles_valid = false;
     h->tiles_fast = fast;
+    h->tiles_want_warps = want_warps;
     h->tiles_usable = false;
     if (h->rows <= 0 || h->cols <= 0) {  // caller-supplied LUT without a declared grid shape: nothing to tile
         h->tiles_valid = true;
@@ -496,7 +509,7 @@ int ensure_tiles(bflk_handle *h, int fast) {
     if (forced == 0 || ((forced == 1 || forced == 2) && h->p_misc.p[forced] <= 5)) mode = forced;
     h->n_tiles = n_tiles;
     h->tile_smax = h->p_misc.p[mode];
-    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast, &h->tuning);
+    h->tile_geom = das_tile_geometry(h->cfg.history, h->max_delay, h->tile_smax, n_tiles, mode, fast, &h->tuning, want_warps);
     // usable: the spread fits a compiled variant, frames are whole blocks, AND the stage ring of some CTA shape fits
     // shared memory (packed rows grow with the largest delay: long arrays fall through to the other kernels)
     h->tiles_usable = h->tile_smax <= das_tile_max_span() && h->cfg.frame_len >= 256 && h->cfg.frame_len % 2 == 0 &&
@@ -613,7 +626,20 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
         return h->fail(BFLK_ERR_INVALID, "bflk_power_map: the FIR reads %d samples past a frame's last tap", h->fir_taps - 2);
     if (!fir && (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4)) {
         // automatic choice = the two-FMA variant (power within the 1e-4 bar); 2 asks for bit-identical delayed sums
-        int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0);
+        // a call with few block pairs cannot fill the SMs with 16-warp CTAs (one cfg3 frame: 16 CTAs, each walking 512
+        // channels with four warps per scheduler): smaller CTAs trade per-SM efficiency for latency.  The shape is part of
+        // the table layout, so a handle that alternates between single frames and large batches rebuilds its tables.
+        int want_warps = 0;
+        if (h->rows > 0 && h->cols > 0 && h->tuning.tile_warps == 0) {
+            const int nblk = N <= 256 ? 1 : (N - 2 + 253) / 254;
+            const long long pairs = ((long long)n_frames * nblk + 1) / 2;
+            const int row0 = (h->dir_first / h->cols) & ~1, row1 = (h->dir_first + h->dir_count - 1) / h->cols;
+            const long long n_tiles = (long long)((row1 - row0) / 2 + 1) * ((h->cols + 1) / 2);
+            if (((n_tiles + 11) / 12) * pairs * 20 < (long long)h->sm_count * 9) {      // even 12-warp CTAs fill < 45 % of the SMs
+                want_warps = ((n_tiles + 7) / 8) * pairs * 20 >= (long long)h->sm_count * 9 ? 8 : 4;
+            }
+        }
+        int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, want_warps);
         if (rc) return rc;
         tiled = h->tiles_usable && (wire || (!(row_stride & 1) && !((uintptr_t)stream_dev & 7)));  // packed rows: 8-byte loads
         if (h->kernel_choice != 0 && !tiled)
@@ -791,10 +817,27 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
         BFLK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->chunk_events.push_back(e);
     }
-    int64_t copied = 0;  // samples per row already on the device
+    // only the samples a frame can touch travel: [history - largest delay, last frame's last tap] -- a third of the
+    // reference's 1024-sample window for a single frame (the rest of d_window is never read)
+    // (a strided copy out of PAGEABLE memory is staged row by row by the driver and loses more than it saves -- measured
+    // cfg3: 289 -> 402 us; pageable single-chunk batches go up as one contiguous copy instead)
+    cudaPointerAttributes attr{};
+    const bool pageable = cudaPointerGetAttributes(&attr, stream) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pageable && n_chunks == 1) {
+        BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, stream, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        rc = power_map_dev(h, h->d_window.p, n_samples, n_samples, n_frames, h->d_power.p, h->stream);
+        if (rc) return rc;
+        BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->last_map_on_device = n_frames == 1;
+        return BFLK_OK;
+    }
+    int64_t copied = pageable ? 0 : std::max<int64_t>(0, (int64_t)(h->cfg.history - h->max_delay) & ~(int64_t)3);  // samples per row already "on the device"
+    const int64_t last_needed = std::min<int64_t>(n_samples, (int64_t)(n_frames - 1) * N + tail + N);
     for (int k = 0; k < n_chunks; k++) {
         const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
-        const int64_t need = std::min<int64_t>(n_samples, k == n_chunks - 1 ? n_samples : (int64_t)(f0 + nf) * N + tail);
+        const int64_t need = k == n_chunks - 1 ? last_needed : std::min<int64_t>(last_needed, (int64_t)(f0 + nf) * N + tail);
         if (need > copied) {
             BFLK_CUDA(h, cudaMemcpy2DAsync(h->d_window.p + copied, n_samples * sizeof(float), stream + copied,
                                            n_samples * sizeof(float), (need - copied) * sizeof(float), C,

@@ -78,7 +78,8 @@ struct Tuning {
 struct TileGeometry {
     int stage_off = 0;   // first packed sample, relative to a block's first output sample (even)
     int nch = 0;         // 16-byte chunks per lane window the kernel variant loads (6, 8 or 10)
-    int warps = 0;       // compute warps (= direction tiles) per CTA of that variant
+    int warps = 0;       // compute warps (= direction tiles) per CTA of the launch
+    int tmpl_warps = 0;  // compiled variant (register budget / launch bound) the launch runs on; >= warps
     int fast = 0;        // 1: two-FMA form (TileEntryFast / TileEntryFastDual tables)
     int mode = 0;        // 0: one window per tile; 1 / 2: one window per direction pair (rows of a column / columns of a row)
     int row_chunks = 0;  // logical chunks per packed row
@@ -177,6 +178,7 @@ struct bflk_handle {
     bool tiles_valid = false;
     bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
     int tiles_fast = 0;          // the tables were built for the two-FMA variant
+    int tiles_want_warps = 0;    // ... and for this CTA shape (0: throughput shape; 4 / 8: latency shape of small calls)
     int32_t n_tiles = 0;
     int32_t tile_smax = 0;       // compiled window slack the tables need
     bflk::DevBuf<char> d_tiles;             // tile_table_entries(n_tiles, usable) TileEntry / TileEntryFast, layout above
@@ -339,7 +341,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
                             void *hook_ctx = nullptr);
 int das_tile_max_span();
 TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles = 0, int mode = 0, int fast = 0,
-                               const Tuning *tuning = nullptr);
+                               const Tuning *tuning = nullptr, int want_warps = 0);
 // shared memory the variant needs with `stages` stage buffers
 size_t das_tile_smem_bytes(const TileGeometry &g, int stages);
 size_t das_tile_packed_bytes(const TileArgs &a);
@@ -382,7 +384,7 @@ cudaError_t launch_map_targets(const float *d_power, int rows, int cols, int max
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold n_samples valid samples
 int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
                   float *power_dev, void *cuda_stream);
-int ensure_tiles(bflk_handle *h, int fast);
+int ensure_tiles(bflk_handle *h, int fast, int want_warps = 0);
 int64_t min_stream_samples(const bflk_handle *h, int n_frames);
 // frames per chunk of a host batch of n_frames (whole CTA waves of the tiled kernel where it applies) and the samples a
 // frame needs beyond its own N

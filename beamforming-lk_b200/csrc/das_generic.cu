@@ -91,9 +91,18 @@ cudaError_t launch_das_generic(const GenericArgs &a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(das_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(a.n_dir, a.n_frames);
-    das_generic_kernel<<<grid, kGenericThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    for (int b0 = 0; b0 < a.n_frames; b0 += 65535) {   // grid.y is limited to 65535
+        GenericArgs s = a;
+        s.n_frames = a.n_frames - b0 < 65535 ? a.n_frames - b0 : 65535;
+        s.stream = a.stream + (size_t)b0 * a.frame_stride;
+        if (a.power) s.power = a.power + (size_t)b0 * a.n_dir;
+        if (a.audio) s.audio = a.audio + (size_t)b0 * a.n_dir * a.frame_len;
+        dim3 grid(a.n_dir, s.n_frames);
+        das_generic_kernel<<<grid, kGenericThreads, smem, st>>>(s);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace bflk

@@ -160,6 +160,7 @@ struct KernelArgs {
     int pair0, n_pairs;          // block pairs [pair0, pair0 + n_pairs) of this launch ...
     int pairs_per_cta;           // ... consecutive ones handled by one CTA (short channel lists: amortises the ramp-up)
     int stages;                  // stage buffers in shared memory (3 or 4)
+    int launch_warps;            // warps per CTA of this launch (host side: <= the compiled variant's)
     float *out;                  // power [frames][n_dir] (blocks_per_frame == 1) or partial [items][n_dir]
     float norm;
 };
@@ -176,15 +177,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     constexpr int kEnt = FAST ? (DUAL ? (int)sizeof(TileEntryFastDual) : (int)sizeof(TileEntryFast)) : (int)sizeof(TileEntry);
     // layout: [stages] x { rows: kCC * row_bytes | tiles: kWarps * kCC * kEnt } then barriers
     const int stage_rows = kCC * a.row_bytes;
-    const int stage_bytes = stage_rows + kWarps * kCC * kEnt;
+    const int stage_bytes = stage_rows + (int)(blockDim.x >> 5) * kCC * kEnt;
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const int kStages = a.stages;
     const uint32_t bars = smem + kStages * stage_bytes;  // full[kStages] mbarriers, then done[kStages] arrival counters
     unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + kStages * stage_bytes + 8 * kStages);
 
+    // kWarps is the compiled register budget (launch bound); a launch may use fewer warps per CTA (single-frame calls:
+    // more, smaller CTAs -- one warp per scheduler instead of four -- cut the latency of the serial channel loop)
+    const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_stage = (a.usable + kCC - 1) / kCC;
-    const int tile0 = blockIdx.x * kWarps;
+    const int tile0 = blockIdx.x * nwarps;
     const int my_tile = min(tile0 + warp, a.n_tiles - 1);
     const bool active = tile0 + warp < a.n_tiles;  // idle warps of the last tile group only keep the pipeline moving
     // this CTA works on block pairs [pair_lo, pair_hi) one after the other; the staging pipeline runs straight through
@@ -209,10 +213,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         const int c0 = st * kCC, nc = min(kCC, a.usable - c0);
         const uint32_t dst = smem + buf * stage_bytes;
         const uint32_t full = bars + 8 * buf;
-        constexpr uint32_t tile_bytes = kWarps * kCC * (uint32_t)kEnt;
+        const uint32_t tile_bytes = (uint32_t)(nwarps * kCC * kEnt);
         mbar_expect_tx(full, (uint32_t)(nc * a.row_bytes) + tile_bytes);
         bulk_g2s(dst, a.packed + ((size_t)pair * a.usable + c0) * a.row_bytes, (uint32_t)(nc * a.row_bytes), full);
-        bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (kWarps * kCC) * kEnt, tile_bytes, full);
+        bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (nwarps * kCC) * kEnt, tile_bytes, full);
     };
     // (pair, chunk) of the stage kStages ahead of the one being consumed, advanced once per stage by every warp
     int npair = pair_lo, nst = 0;
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         __syncwarp();
         if (lane == 0) {
             // all of this warp's reads of the buffer have completed (their values were consumed above)
-            if (atomicInc(&done_cnt[buf], kWarps - 1) == kWarps - 1 && npair < pair_hi) issue(npair, nst, buf);
+            if (atomicInc(&done_cnt[buf], nwarps - 1) == (unsigned)(nwarps - 1) && npair < pair_hi) issue(npair, nst, buf);
         }
         if (++nst == n_stage) { nst = 0; npair++; }
         if (++buf == kStages) { buf = 0; ph ^= 1; }
@@ -335,7 +339,7 @@ size_t das_tile_smem_bytes(const TileGeometry &g, int stages) {
     return (size_t)stages * (kCC * g.row_bytes + g.warps * kCC * das_tile_entry_bytes(g)) + stages * (8 + 4) + 96;
 }
 
-TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast, const Tuning *tuning) {
+TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast, const Tuning *tuning, int want_warps) {
     TileGeometry g;
     g.mode = mode;
     g.fast = fast;
@@ -380,7 +384,21 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
         const double score = (forced ? 1.0 : tlp[i]) * tiles / (double)(groups * cand[i]);
         if (score > best + 1e-9) { best = score; g.warps = cand[i]; g.stages = stages; }
     }
-    if (g.warps == 0) g.warps = 12;   // nothing fits: stages stays 0
+    g.tmpl_warps = g.warps;
+    if (want_warps > 0 && want_warps < 10 && g.stages >= 3) {
+        // latency shape (single-frame calls): fewer warps per CTA than the throughput shape, run on the largest compiled
+        // variant (its register budget is an upper bound); the stage ring of a smaller CTA always fits if the large one does
+        TileGeometry t = g;
+        t.warps = want_warps;
+        int stages = tuning && tuning->tile_stages == 3 ? 3 : kMaxStages;
+        if (das_tile_smem_bytes(t, stages) > 227 * 1024) stages = 3;
+        if (das_tile_smem_bytes(t, stages) <= 227 * 1024) {
+            g.tmpl_warps = can16 && !exact_dual7 ? 16 : 12;
+            g.warps = want_warps;
+            g.stages = stages;
+        }
+    }
+    if (g.warps == 0) g.warps = g.tmpl_warps = 12;   // nothing fits: stages stays 0
     g.pairs_per_cta = tuning && tuning->tile_pairs > 0 ? tuning->tile_pairs : 0;
     return g;
 }
@@ -391,9 +409,14 @@ size_t das_tile_entry_bytes(const TileGeometry &g) {
 
 template <int NCH, int WARPS, bool DUAL = false, bool FAST = false>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    das_tile_kernel<NCH, WARPS, DUAL, FAST><<<grid, WARPS * 32, smem, st>>>(k);
+    static size_t configured = 0;   // the attribute only ever grows: set it when a larger request appears, not per launch
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int warps = k.launch_warps > 0 && k.launch_warps <= WARPS ? k.launch_warps : WARPS;
+    das_tile_kernel<NCH, WARPS, DUAL, FAST><<<grid, warps * 32, smem, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -429,6 +452,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     p.copy_bytes = a.geom.copy_bytes;
     p.packed = reinterpret_cast<float4 *>(a.packed);
     const int kWarps = a.geom.warps;
+    const int tw = a.geom.tmpl_warps;   // compiled variant (register budget) the launch uses
     const int stages = a.geom.stages;
     if (stages < 3) return cudaErrorInvalidConfiguration;   // ensure_tiles never selects such a geometry
     const size_t smem = das_tile_smem_bytes(a.geom, stages);
@@ -447,6 +471,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     k.out = nblk == 1 ? a.power : a.partial;
     k.norm = a.norm;
     k.stages = stages;
+    k.launch_warps = kWarps;
 
     // grid.y / grid.z are limited to 65535: process the pairs in slabs
     const int max_slab = 32768;
@@ -471,14 +496,14 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         if (hook) hook(hook_ctx, 0, true, st);
         if (a.geom.fast && a.geom.mode != 0) {
             if (a.geom.nch == 6) {
-                switch (a.geom.warps) {
+                switch (tw) {
                     case 10: e = launch_main<6, 10, true, true>(ks, grid, smem, st); break;
                     case 11: e = launch_main<6, 11, true, true>(ks, grid, smem, st); break;
                     case 12: e = launch_main<6, 12, true, true>(ks, grid, smem, st); break;
                     default: e = launch_main<6, 16, true, true>(ks, grid, smem, st); break;
                 }
             } else {
-                switch (a.geom.warps) {
+                switch (tw) {
                     case 10: e = launch_main<7, 10, true, true>(ks, grid, smem, st); break;
                     case 11: e = launch_main<7, 11, true, true>(ks, grid, smem, st); break;
                     case 12: e = launch_main<7, 12, true, true>(ks, grid, smem, st); break;
@@ -488,7 +513,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         } else if (a.geom.fast) {
             switch (a.geom.nch) {
 #define BFLK_LAUNCH_FAST(NCH)                                                          \
-    switch (a.geom.warps) {                                                            \
+    switch (tw) {                                                            \
         case 10: e = launch_main<NCH, 10, false, true>(ks, grid, smem, st); break;     \
         case 11: e = launch_main<NCH, 11, false, true>(ks, grid, smem, st); break;     \
         case 16: e = launch_main<NCH, 16, false, true>(ks, grid, smem, st); break;     \
@@ -504,14 +529,14 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
             }
         } else if (a.geom.mode != 0) {
             if (a.geom.nch == 6) {
-                switch (a.geom.warps) {
+                switch (tw) {
                     case 10: e = launch_main<6, 10, true>(ks, grid, smem, st); break;
                     case 11: e = launch_main<6, 11, true>(ks, grid, smem, st); break;
                     case 12: e = launch_main<6, 12, true>(ks, grid, smem, st); break;
                     default: e = launch_main<6, 16, true>(ks, grid, smem, st); break;
                 }
             } else {
-                switch (a.geom.warps) {
+                switch (tw) {
                     case 10: e = launch_main<7, 10, true>(ks, grid, smem, st); break;
                     case 11: e = launch_main<7, 11, true>(ks, grid, smem, st); break;
                     default: e = launch_main<7, 12, true>(ks, grid, smem, st); break;
@@ -520,7 +545,7 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         } else
         switch (a.geom.nch) {
 #define BFLK_LAUNCH(NCH)                                                              \
-    switch (a.geom.warps) {                                                            \
+    switch (tw) {                                                            \
         case 10: e = launch_main<NCH, 10>(ks, grid, smem, st); break;                  \
         case 11: e = launch_main<NCH, 11>(ks, grid, smem, st); break;                  \
         case 16: e = launch_main<NCH, 16>(ks, grid, smem, st); break;                  \

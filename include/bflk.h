@@ -86,6 +86,10 @@ int bflk_set_channel_mask(bflk_handle *h, const int32_t *index, int32_t usable);
 int bflk_set_grid_fov(bflk_handle *h, int32_t rows, int32_t cols, float fov_deg);
 /* Caller-supplied LUT [D][C] (physical element index), offsets as in the reference (H - int(delay)). */
 int bflk_set_grid_tables(bflk_handle *h, const int32_t *offsets, const float *fractions, int32_t n_directions);
+/* Declares that a caller-supplied LUT is a row-major rows x cols grid of neighbouring directions (rows * cols = D): the
+ * register-tiled kernels, which share sample windows inside 2x2 tiles of adjacent directions, then serve it like a
+ * bflk_set_grid_fov grid; without it such tables run on the lane-broadcast kernel. */
+int bflk_set_grid_shape(bflk_handle *h, int32_t rows, int32_t cols);
 /* Multi-GPU sharding: this handle computes directions [first, first+count) of the grid only. */
 int bflk_set_direction_range(bflk_handle *h, int32_t first, int32_t count);
 int bflk_get_n_directions(const bflk_handle *h, int32_t *total, int32_t *first, int32_t *count);

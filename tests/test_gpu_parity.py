@@ -561,7 +561,17 @@ def test_caller_supplied_tables_and_errors(bf, oracle):
     b.set_grid_tables(off, fr)
     from bflk import synth
     window = synth.make_stream(xyz, 1024)
-    assert rel_err(b.power_map(window), oracle.mimo_update(window, off, fr)) <= POWER_RTOL
+    po = oracle.mimo_update(window, off, fr)
+    p_list = b.power_map(window)
+    assert rel_err(p_list, po) <= POWER_RTOL and b.kernel_info()[0] == 3     # a bare direction list: lane-broadcast kernel
+    with pytest.raises(bflk.BflkError):
+        b.set_grid_shape(7, 10)                                  # not the 60 directions of the tables
+    b.set_grid_shape(6, 10)                                      # declared as a grid: the register-tiled kernels serve it
+    p_grid = b.power_map(window)
+    assert b.kernel_info()[0] == 4 and rel_err(p_grid, po) <= POWER_RTOL
+    b.set_kernel(2)
+    assert rel_err(b.power_map(window), po) <= POWER_RTOL and b.kernel_info()[0] == 2
+    b.set_kernel(0)
     bad = off.copy()
     bad[3, 5] = -1
     with pytest.raises(bflk.BflkError) as e:
@@ -575,6 +585,36 @@ def test_caller_supplied_tables_and_errors(bf, oracle):
         far.set_tiled_geometry(np.array([[-1.0, 0, 0], [1.0, 0, 0]], np.float32))
         far.set_grid_fov(8, 8, 180.0)
     assert e.value.code == -5
+
+
+def test_long_array_falls_back_when_the_stage_ring_does_not_fit(bf, oracle):
+    """Eight arrays in a row (512 microphones, 1.28 m): delays up to ~182 samples make the packed rows of the tiled kernel
+    too long for its shared-memory stage ring with 16 warps.  The automatic choice must pick a shape that fits or fall
+    through to another kernel -- never fail -- and agree with the oracle."""
+    org = cases.origins(8, 1)
+    w = bf.MIMOWorker(org, 16, 16, 180.0)
+    from bflk import synth
+    xyz = synth.tile_geometry(org)
+    window = synth.make_stream(xyz, 1024)
+    off, fr = w.tables()
+    assert (256 - off).max() > 150                               # the geometry really is that long
+    po = oracle.mimo_update(window, off, fr)
+    p = w.update(window)
+    assert rel_err(p, po) <= POWER_RTOL and int(np.argmax(p)) == int(np.argmax(po))
+    B = 6
+    stream = synth.make_stream(xyz, (B - 1) * 256 + 1024)
+    pb = w.power_map_batch(stream, B)                            # throughput shape of the same grid
+    for b_ in (0, B - 1):
+        wref = oracle.mimo_update(np.ascontiguousarray(stream[:, b_ * 256: b_ * 256 + 1024]), off, fr)
+        assert rel_err(pb[b_], wref) <= POWER_RTOL
+    for k in (1, 3):                                             # the kernels it may fall back to
+        w.set_kernel(k)
+        assert rel_err(w.update(window), po) <= POWER_RTOL
+    # a finer grid of the same array: larger table, same row length
+    w2 = bf.MIMOWorker(org, 64, 64, 180.0)
+    off2, fr2 = w2.tables()
+    sel = np.arange(0, 4096, 41)
+    assert rel_err(w2.update(window)[sel], oracle.mimo_update(window, off2[sel], fr2[sel])) <= POWER_RTOL
 
 
 def test_resize_and_targets_after_the_map(bf, oracle, golden):
