@@ -138,11 +138,9 @@ cudaError_t launch_das_miso(const MisoArgs &a, cudaStream_t st) {
     if (a.n_targets <= 0 || a.n_frames <= 0) return cudaSuccess;
     const size_t smem = (size_t)a.usable * (sizeof(long long) + sizeof(float)) + (size_t)a.C * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-    static size_t configured = 48 * 1024;   // the attribute only ever grows; set it when a larger request appears, not per launch
-    if (smem > configured) {
+    if (smem > 48 * 1024) {   // beyond the default limit (thousands of channels): per device, so set per launch
         cudaError_t e = cudaFuncSetAttribute(miso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int n_slices = das_miso_slices(a.frame_len);
     for (int b0 = 0; b0 < a.n_frames; b0 += 65535) {   // grid.z is limited to 65535

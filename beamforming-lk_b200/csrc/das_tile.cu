@@ -409,11 +409,14 @@ size_t das_tile_entry_bytes(const TileGeometry &g) {
 
 template <int NCH, int WARPS, bool DUAL = false, bool FAST = false>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;   // the attribute only ever grows: set it when a larger request appears, not per launch
-    if (smem > configured) {
+    // the attribute is per device and only ever grows: set it when a larger request appears there, not per launch
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
     const int warps = k.launch_warps > 0 && k.launch_warps <= WARPS ? k.launch_warps : WARPS;
     das_tile_kernel<NCH, WARPS, DUAL, FAST><<<grid, warps * 32, smem, st>>>(k);
