@@ -234,42 +234,51 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
 #pragma unroll
         for (int k = 0; k < kK; k++) acc[r][k] = 0ull;
 
-    for (int st = 0; st < n_stage; st++) {
-        mbar_wait(bars + 8 * buf, ph);
-        const uint32_t rows_s = smem + buf * stage_bytes;
-        const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * kEnt;
-        const int nc = min(kCC, a.usable - st * kCC);
-        if constexpr (FAST) {
-            // the whole stage in one asm block: entry prefetch, window loads, four dispatched bodies, loop
+    // one pipeline stage (kCC channels).  Whether the stage loop is left to the compiler's loop transformations changes how
+    // ptxas allocates the 64 accumulator registers around the PTX block: measured on B200, the two-window variants are
+    // 3 % faster with the loop kept as written (no in-loop register moves), the one-window variants 9 % slower.
+    auto stage = [&](int st) {
+            mbar_wait(bars + 8 * buf, ph);
+            const uint32_t rows_s = smem + buf * stage_bytes;
+            const uint32_t tiles_s = rows_s + stage_rows + warp * kCC * kEnt;
+            const int nc = min(kCC, a.usable - st * kCC);
+            if constexpr (FAST) {
+                // the whole stage in one asm block: entry prefetch, window loads, four dispatched bodies, loop
+                if (active) {
+                    // (the entries' window offsets include the row's offset inside the stage)
+                    if constexpr (DUAL) tile_stage_fast_dual<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
+                    else tile_stage_fast<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
+                }
+            } else
             if (active) {
-                // (the entries' window offsets include the row's offset inside the stage)
-                if constexpr (DUAL) tile_stage_fast_dual<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
-                else tile_stage_fast<NCH>(acc, tiles_s, rows_s + lane_off, tiles_s + nc * kEnt);
-            }
-        } else
-        if (active) {
-            uint32_t e0, e1;
-            float f0, f1, f2, f3;
-            uint32_t ent = tiles_s, row = rows_s + lane_off;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(ent));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(ent + 16));
+                uint32_t e0, e1;
+                float f0, f1, f2, f3;
+                uint32_t ent = tiles_s, row = rows_s + lane_off;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(ent));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f0), "=f"(f1), "=f"(f2), "=f"(f3) : "r"(ent + 16));
 #pragma unroll 1
-            for (int c = 0; c < nc; c++) {
-                // window loads, differences, four accumulate bodies, prefetch of entry c + 1 into e0..f3 (the read past
-                // the last entry of a stage stays inside this CTA's shared memory and is never used)
-                ent += 32;
-                if constexpr (DUAL) tile_channel_step_dual<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
-                else tile_channel_step<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
-                row += a.row_bytes;
+                for (int c = 0; c < nc; c++) {
+                    // window loads, differences, four accumulate bodies, prefetch of entry c + 1 into e0..f3 (the read past
+                    // the last entry of a stage stays inside this CTA's shared memory and is never used)
+                    ent += 32;
+                    if constexpr (DUAL) tile_channel_step_dual<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
+                    else tile_channel_step<NCH>(acc, e0, e1, f0, f1, f2, f3, row, ent);
+                    row += a.row_bytes;
+                }
             }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            // all of this warp's reads of the buffer have completed (their values were consumed above)
-            if (atomicInc(&done_cnt[buf], nwarps - 1) == (unsigned)(nwarps - 1) && npair < pair_hi) issue(npair, nst, buf);
-        }
-        if (++nst == n_stage) { nst = 0; npair++; }
-        if (++buf == kStages) { buf = 0; ph ^= 1; }
+            __syncwarp();
+            if (lane == 0) {
+                // all of this warp's reads of the buffer have completed (their values were consumed above)
+                if (atomicInc(&done_cnt[buf], nwarps - 1) == (unsigned)(nwarps - 1) && npair < pair_hi) issue(npair, nst, buf);
+            }
+            if (++nst == n_stage) { nst = 0; npair++; }
+            if (++buf == kStages) { buf = 0; ph ^= 1; }
+    };
+    if constexpr (DUAL && FAST) {
+#pragma unroll 1
+        for (int st = 0; st < n_stage; st++) stage(st);
+    } else {
+        for (int st = 0; st < n_stage; st++) stage(st);
     }
 
     // ---- epilogue: MA = 0.5 out[j] - 0.25 (out[j+1] + out[j-1]); power = sum MA^2 (mimo.cpp:131-137) ----

@@ -560,7 +560,21 @@ def run_ours(args, c, name):
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         ems = float(ems.item())
-        e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": C * T * 4 if world == 1 else
+        # what the PCIe links deliver when every rank uploads at once (the e2e path moves C*T*4 bytes per step in total)
+        probe_bytes = min(host_in.numel() * 4, 64 << 20)
+        probe_dev = torch.empty(probe_bytes // 4, dtype=torch.float32, device=dev)
+        probe_src = host_in.view(-1)[:probe_bytes // 4]
+        probe_dev.copy_(probe_src, non_blocking=True)
+        tm.barrier()
+        tp = time.perf_counter()
+        for _ in range(8):
+            probe_dev.copy_(probe_src, non_blocking=True)
+        tm.barrier()
+        h2d_gbs = torch.tensor([8 * probe_bytes / (time.perf_counter() - tp) / 1e9], device=dev)
+        if world > 1:
+            dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
+        del probe_dev
+        e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_gbs_per_rank_all_ranks_uploading": float(h2d_gbs.item()), "h2d_bytes_per_step": C * T * 4 if world == 1 else
                C * (B * N + gf * (c["W"] - N)) * 4, "d2h_bytes_per_step": B * D * 4 * world, "steps": e2e_steps,
                "path": "bflk_power_map_batch (host buffers)" if world == 1 else
                "bflk_power_map_batch_sharded: per frame chunk each rank uploads C/G_d channel rows over its own PCIe link, NCCL all-gather "

@@ -35,9 +35,11 @@ ADD_AS_FMA = os.environ.get("BFLK_GEN_ADD_AS_FMA", "0") == "1"
 # (shared memory is already 81 % busy there; earlier loads only lengthen its queue) -> "single"
 PIPE_MODE = os.environ.get("BFLK_GEN_PIPE", "single")
 # two-FMA variants: one loop tail (fraction prefetch, next window addresses, loop branch) shared by all last-direction
-# bodies instead of a copy per body.  ptxas then coalesces the accumulators across the back edge (26 -> 8 MOVs in the
-# two-window loop); measured +0.3 .. +0.5 % for the two-window flavour, -1.5 % for the single-window one -> "dual"
-SHARED_TAIL = os.environ.get("BFLK_GEN_SHARED_TAIL", "dual")
+# bodies ("1"), or a copy per body ("0"); "dual" = shared for the two-window flavour only.  Round 1 measured the shared
+# tail +0.3 .. +0.5 % for the two-window flavour (fewer register moves across the back edge); with the round-2 stage loop
+# (last-arriver refill) ptxas splits the live ranges of four accumulators of the second direction around the shared tail
+# instead (8 MOVs per channel): a tail per body removes them, cfg3 0.559 -> 0.577, cfg2 0.600 -> 0.620 -> "0"
+SHARED_TAIL = os.environ.get("BFLK_GEN_SHARED_TAIL", "0")
 # wide flavour (gen_wide): next channel's window loads from inside the last body (same idea as PIPE_MODE)
 PIPE_MODE_WIDE = os.environ.get("BFLK_GEN_PIPE_WIDE", "0")
 
