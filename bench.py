@@ -546,8 +546,15 @@ def run_ours(args, c, name):
             def e2e_step():
                 w.power_map_batch_ptr(host_in.data_ptr(), T, B, host_out.data_ptr())
         else:
+            # host batches want chunks of whole CTA waves that are as short as possible (upload of chunk k+1 under the kernels of
+            # chunk k): with 4 direction groups a wave of a rank's 64 tiles is 37 block pairs, so an 8-rank job cuts its frame
+            # slices into four one-wave chunks instead of two two-wave chunks (the resident path prefers 2 groups: less pack)
+            e2e_gd = 4 if (world % 4 == 0 and world >= 8 and args.dir_groups == 0) else args.dir_groups
+            we = make_worker(e2e_gd) if e2e_gd != args.dir_groups else w
+            out_ptr = host_out.data_ptr() if rank == 0 else 0      # the maps are read back where they are consumed: rank 0
+
             def e2e_step():
-                w.power_map_batch_sharded_ptr(host_in.data_ptr(), T, B, host_out.data_ptr())
+                we.power_map_batch_sharded_ptr(host_in.data_ptr(), T, B, out_ptr)
         e2e_steps = max(3, min(args.steps, 40) // 2)
         e2e_step()
         tm.barrier()
@@ -575,12 +582,14 @@ def run_ours(args, c, name):
             dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
         del probe_dev
         e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_gbs_per_rank_all_ranks_uploading": float(h2d_gbs.item()), "h2d_bytes_per_step": C * T * 4 if world == 1 else
-               C * (B * N + gf * (c["W"] - N)) * 4, "d2h_bytes_per_step": B * D * 4 * world, "steps": e2e_steps,
+               C * (B * N + gf * (c["W"] - N)) * 4, "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
                "path": "bflk_power_map_batch (host buffers)" if world == 1 else
                "bflk_power_map_batch_sharded: per frame chunk each rank uploads C/G_d channel rows over its own PCIe link, NCCL all-gather "
                "inside the frame group (copy stream) overlapping the kernels of the previous chunk, NCCL all-gather of the maps, D2H of "
-               "[B][D] on every rank; bytes summed over the ranks",
-               "same_maps_as_resident_path": bool(torch.equal(host_out, ref_maps.cpu()))}
+               "[B][D] on rank 0; h2d bytes summed over the ranks" + (f"; {we.comm_info()[2]} direction groups x {we.comm_info()[3]} frame groups" if world > 1 else ""),
+               "same_maps_as_resident_path": bool(torch.equal(host_out, ref_maps.cpu())) if rank == 0 else None}
+        if world > 1 and we is not w:
+            we.close()
 
     # ---- the other split (pure grid sharding, the north_star's) in the same run ----
     grid_shard = None

@@ -765,6 +765,151 @@ __device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[2][{KW}], uint32_t ent,
 """
 
 
+
+def gen_k16(nch, dual=False):
+    """Two-FMA form with SIXTEEN sample pairs per lane (512-sample blocks) and the usual 2x2 direction tile: 128 accumulator
+    registers, so 8 warps per CTA at 255 registers -- but per (warp, channel) 128 FFMA2 behind the same four dispatches, the
+    same entry loads and a window only 25 % longer than the 8-pair flavour's: half the non-FP instructions and ~0.8x the
+    shared-memory wavefronts per FLOP.  Packed rows carry one 16-byte pad per EIGHT chunks (lane stride 9 chunks = 144 B),
+    eight pad classes.  Structure as gen_fast (one chain per delta value, loop tail per body, no pipelined window loads).
+    operands: acc[4][16] "+l" 0..63, ent 64 "+r", row 65 "r", end 66 "r".
+    entry (single, 80 B): o[8] | f[4] | g[4] | dl, -, -, -;   (dual, 112 B): oA[8] | oB[8] | f[4] | g[4] | dl, -, -, -"""
+    KW = 16
+    nw = 2 * nch
+    kmax = nw - (KW + 1)
+    assert kmax >= 0
+    nbits = max(1, kmax.bit_length())
+    ENT, ROWR, END = "%64", "%65", "%66"
+    esz = 112 if dual else 80
+    o_f, o_g, o_dl = (64, 80, 96) if dual else (32, 48, 64)
+    AW = lambda r, k: f"%{r * KW + k}"
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        for k in range(KW):
+            emit(f"    fma.rn.f32x2 {AW(r, k)}, gg{r}, w{D + k + 1}, {AW(r, k)};")
+        for k in range(KW):
+            emit(f"    fma.rn.f32x2 {AW(r, k)}, ff{r}, w{D + k}, {AW(r, k)};")
+
+    def preds(r):
+        for b in range(nbits):
+            emit(f"    and.b32 x, dl, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 p{b}, x, 0;")
+
+    def window(o):
+        for m in range(nch):
+            emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [{o}{m & 7}+{16 * (m + (m >> 3))}];")
+
+    def load_entry_head():
+        emit(f"    ld.shared.v4.u32 {{oa0, oa1, oa2, oa3}}, [{ENT}];")
+        emit(f"    ld.shared.v4.u32 {{oa4, oa5, oa6, oa7}}, [{ENT}+16];")
+        if dual:
+            emit(f"    ld.shared.v4.u32 {{ob0, ob1, ob2, ob3}}, [{ENT}+32];")
+            emit(f"    ld.shared.v4.u32 {{ob4, ob5, ob6, ob7}}, [{ENT}+48];")
+        emit(f"    ld.shared.u32 dl, [{ENT}+{o_dl}];")
+
+    def load_entry_fracs():
+        emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+{o_f}];")
+        emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+{o_g}];")
+
+    def entry_tail():
+        for c in range(8):
+            emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+        preds(0)
+
+    def subtree(r, lo, bit, tag):
+        if bit < 0:
+            emit(f"    bra.uni B{r}_{lo};")
+            return
+        hi = lo + (1 << bit)
+        if hi > kmax:
+            subtree(r, lo, bit - 1, tag)
+            return
+        lab = f"T{tag}_{hi}_{bit}"
+        emit(f"    @p{bit} bra.uni {lab};")
+        subtree(r, lo, bit - 1, tag)
+        emit(f"{lab}:")
+        subtree(r, hi, bit - 1, tag)
+
+    need = set()
+
+    def tree_from(r, dd):
+        for b in reversed(range(nbits)):
+            want = (dd >> b) & 1
+            base = ((dd >> (b + 1)) << (b + 1)) | ((1 - want) << b)
+            if base > kmax:
+                continue
+            need.add((r, base, b))
+            emit(f"    @{'!' if want else ''}p{b} bra.uni S{r}_{base}_{b};")
+
+    emit("{")
+    emit(f"    .reg .pred p<{nbits}>, ploop, q;")
+    emit("    .reg .b32 x, dl, oa<8>, ob<8>;")
+    emit("    .reg .f32 f<4>, g<4>;")
+    emit(f"    .reg .b64 ff<4>, gg<4>, w<{nw}>;")
+    load_entry_head()
+    load_entry_fracs()
+    entry_tail()
+    emit("TOP:")
+    window("oa")
+    for r in range(4):
+        emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
+        emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
+    tree_from(0, 0)
+    for dd in range(kmax + 1):
+        for r in range(4):
+            emit(f"B{r}_{dd}:")
+            if r == 0:
+                preds(1)
+                body(r, dd)
+                tree_from(1, dd)
+            elif r == 1:
+                preds(2)
+                if dual:
+                    emit(f"    and.b32 x, dl, {1 << 28};")
+                    emit("    setp.ne.b32 q, x, 0;")
+                body(r, dd)
+                if dual:
+                    emit(f"    @q bra.uni SW_{dd};")
+                    for c in range(8):
+                        emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
+                    window("ob")
+                    emit(f"SW_{dd}:")
+                tree_from(2, dd)
+            elif r == 2:
+                preds(3)
+                body(r, dd)
+                tree_from(3, dd)
+            else:
+                emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+                load_entry_head()
+                emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
+                body(r, dd)
+                load_entry_fracs()
+                entry_tail()
+                emit("    @ploop bra.uni TOP;")
+                emit("    bra.uni DONE;")
+    for (r, base, b) in sorted(need):
+        emit(f"S{r}_{base}_{b}:")
+        subtree(r, base, b - 1, f"{r}_{base}_{b}")
+    emit("DONE:")
+    emit("}")
+    asm = "\n".join(f'        "{ln}\\n"' for ln in L)
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(KW)] + ['"+r"(ent)'])
+    name = "tile_stage_k16_dual" if dual else "tile_stage_k16"
+    return f"""// NCH = {nch}: 16 sample pairs per lane, {'two windows' if dual else 'window'} of {nw} sample pairs, deltas 0..{kmax}
+template <>
+__device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[4][{KW}], uint32_t ent, uint32_t row, uint32_t end) {{
+    asm volatile(
+{asm}
+        : {outs}
+        : "r"(row), "r"(end)
+        : "memory");
+}}
+"""
+
+
 # Measured and rejected: a double-buffered flavour (window B of a channel in flight to a second register set while slots
 # 0,1 run on window A, then window A of the next channel while slots 2,3 run): ~165 registers -> 12 warps per CTA (the
 # register file is split per scheduler, so 14 warps still cap a thread at 128), always two window loads per channel ->
@@ -784,6 +929,19 @@ __device__ __forceinline__ void tile_stage_fast_dual(u64 (&acc)[4][8], uint32_t 
         print(gen_fast(nch))
     for nch in (6, 7):
         print(gen_fast(nch, dual=True))
+    sys.exit(0)
+if "--k16" in sys.argv:
+    print("// GENERATED by tools/gen_tile_asm.py --k16 -- do not edit.  See that script for the why.")
+    print("""// All channels of one pipeline stage for one 2x2 tile, 16 sample pairs per lane (512-sample blocks), two-FMA form.
+template <int NCH>
+__device__ __forceinline__ void tile_stage_k16(u64 (&acc)[4][16], uint32_t ent, uint32_t row, uint32_t end);
+template <int NCH>
+__device__ __forceinline__ void tile_stage_k16_dual(u64 (&acc)[4][16], uint32_t ent, uint32_t row, uint32_t end);
+""")
+    for nch in (9, 10, 11):
+        print(gen_k16(nch))
+    for nch in (10, 11):
+        print(gen_k16(nch, dual=True))
     sys.exit(0)
 if "--wide" in sys.argv:
     print("// GENERATED by tools/gen_tile_asm.py --wide -- do not edit.  See that script for the why.")

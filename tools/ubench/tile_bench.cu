@@ -28,8 +28,9 @@ typedef unsigned long long u64;
 #define WIDE_INC "wide_default.inc"   // python ../gen_tile_asm.py --wide > wide_default.inc
 #endif
 #include WIDE_INC
+#include "k16.inc"   // python ../gen_tile_asm.py --k16 > k16.inc
 
-enum Variant { FAST_SINGLE = 0, FAST_DUAL = 1, WIDE = 2, WIDE_EXACT = 3, EXACT_SINGLE = 4, EXACT_DUAL = 5 };
+enum Variant { FAST_SINGLE = 0, FAST_DUAL = 1, WIDE = 2, WIDE_EXACT = 3, EXACT_SINGLE = 4, EXACT_DUAL = 5, K16_SINGLE = 6, K16_DUAL = 7 };
 
 struct Args {
     const char *entries;   // [n_sets][warps][cc][ent]
@@ -51,9 +52,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) bench_kernel(Args a) {
     for (int i = threadIdx.x; i < a.n_sets * set_bytes / 4; i += blockDim.x)
         reinterpret_cast<uint32_t *>(ents)[i] = reinterpret_cast<const uint32_t *>(a.entries)[i];
     __syncthreads();
-    u64 acc[32];
+    constexpr int NACC = (V == K16_SINGLE || V == K16_DUAL) ? 64 : 32;
+    u64 acc[NACC];
 #pragma unroll
-    for (int i = 0; i < 32; i++) acc[i] = 0ull;
+    for (int i = 0; i < NACC; i++) acc[i] = 0ull;
     const uint32_t rows_s = smem, ents_s = smem + a.rows_bytes;
     long long t0, t1;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) bench_kernel(Args a) {
         if constexpr (V == FAST_SINGLE) tile_stage_fast<NCH>(*reinterpret_cast<u64(*)[4][8]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == FAST_DUAL) tile_stage_fast_dual<NCH>(*reinterpret_cast<u64(*)[4][8]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == WIDE) tile_stage_wide<NCH>(*reinterpret_cast<u64(*)[2][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
+        if constexpr (V == K16_SINGLE) tile_stage_k16<NCH>(*reinterpret_cast<u64(*)[4][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
+        if constexpr (V == K16_DUAL) tile_stage_k16_dual<NCH>(*reinterpret_cast<u64(*)[4][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == WIDE_EXACT) tile_stage_wide_exact<NCH>(*reinterpret_cast<u64(*)[2][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == EXACT_SINGLE || V == EXACT_DUAL) {
             uint32_t e0, e1;
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) bench_kernel(Args a) {
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; i++) s += __uint_as_float((unsigned)acc[i]) + __uint_as_float((unsigned)(acc[i] >> 32));
+    for (int i = 0; i < NACC; i++) s += __uint_as_float((unsigned)acc[i]) + __uint_as_float((unsigned)(acc[i] >> 32));
     a.out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     __shared__ long long smin, smax;
     if (threadIdx.x == 0) { smin = t0; smax = t1; }
@@ -103,12 +107,13 @@ static const double kTileSpanFine[2] = {0.65, 0.35};
 
 template <int V, int NCH, int WARPS>
 static void run(const char *name, int sms, int max_q, double same_window_share, const double *span_p, int n_span) {
-    const int cc = (V == WIDE || V == WIDE_EXACT) ? 4 : 8;
-    const int lane_chunks = (V == WIDE || V == WIDE_EXACT) ? 8 : 4;
+    constexpr bool k16 = V == K16_SINGLE || V == K16_DUAL;
+    const int cc = (V == WIDE || V == WIDE_EXACT || k16) ? 4 : 8;
+    const int lane_chunks = (V == WIDE || V == WIDE_EXACT || k16) ? 8 : 4;
     const int row_chunks = max_q + lane_chunks * 31 + NCH + 1;
     const int copy_bytes = 16 * ((lane_chunks == 8 ? padded8(row_chunks - 1) : padded4(row_chunks - 1)) + 1);
     const int row_bytes = 2 * copy_bytes;
-    const int ent_bytes = V == FAST_SINGLE ? 64 : V == FAST_DUAL ? 80 : (V == WIDE || V == WIDE_EXACT) ? 48 : 32;
+    const int ent_bytes = V == FAST_SINGLE ? 64 : V == FAST_DUAL ? 80 : (V == WIDE || V == WIDE_EXACT) ? 48 : V == K16_SINGLE ? 80 : V == K16_DUAL ? 112 : 32;
     const int n_sets = 8;
     std::mt19937 rng(12345);
     auto pick_span = [&]() {
@@ -124,7 +129,26 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
                 auto window = [&](int &odd, int &q) { odd = rng() & 1; q = rng() % (max_q + 1); };
                 float fr[4];
                 for (int k = 0; k < 4; k++) fr[k] = std::uniform_real_distribution<float>(0, 1)(rng);
-                if (V == WIDE || V == WIDE_EXACT) {
+                if (k16) {
+                    uint32_t oa[8], ob[8], dl = 0;
+                    float g[4];
+                    for (int k = 0; k < 4; k++) g[k] = 1.0f - fr[k];
+                    for (int w2 = 0; w2 < (V == K16_DUAL ? 2 : 1); w2++) {
+                        int odd, q; window(odd, q);
+                        const int r = q & 7;
+                        for (int k = 0; k < 8; k++) (w2 ? ob : oa)[k] = c * row_bytes + odd * copy_bytes + 16 * padded8(q) + ((k > 0 && r + k >= 8) ? 16 : 0);
+                        const int sp = pick_span();
+                        if (V == K16_DUAL) dl |= ((rng() & 1) ? (uint32_t)sp : ((uint32_t)sp << 6)) << (12 * w2);
+                        else {
+                            const int zero_slot = rng() & 3;
+                            for (int k = 0; k < 4; k++) dl |= (uint32_t)(k == zero_slot ? 0 : (sp ? rng() % (sp + 1) : 0)) << (6 * k);
+                            if (sp) dl = (dl & ~(63u << (6 * ((zero_slot + 1) & 3)))) | ((uint32_t)sp << (6 * ((zero_slot + 1) & 3)));
+                        }
+                    }
+                    if (V == K16_DUAL && std::uniform_real_distribution<double>(0, 1)(rng) < same_window_share) dl |= 1u << 28;
+                    if (V == K16_DUAL) { memcpy(e, oa, 32); memcpy(e + 32, ob, 32); memcpy(e + 64, fr, 16); memcpy(e + 80, g, 16); memcpy(e + 96, &dl, 4); }
+                    else { memcpy(e, oa, 32); memcpy(e + 32, fr, 16); memcpy(e + 48, g, 16); memcpy(e + 64, &dl, 4); }
+                } else if (V == WIDE || V == WIDE_EXACT) {
                     int odd, q; window(odd, q);
                     const int r = q & 7, sp = pick_span();
                     uint32_t o[8];
@@ -186,7 +210,7 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
     CK(cudaMemcpy(cyc.data(), d_cyc, sms * 8, cudaMemcpyDeviceToHost));
     std::sort(cyc.begin(), cyc.end());
     const double c = (double)cyc[sms / 2], steps = (double)a.iters * cc;
-    const double frac = steps * 64 * 2 * (WARPS / 4.0) / c;
+    const double frac = steps * (k16 ? 128 : 64) * 2 * (WARPS / 4.0) / c;
     printf("%-28s nch %2d warps %2d row %5d B  cycles/channel-step/warp %.1f  fraction of FFMA2 issue peak %.3f\n", name, NCH, WARPS,
            row_bytes, c / steps, frac);
     cudaFree(d_ents); cudaFree(d_out); cudaFree(d_cyc);
@@ -210,6 +234,12 @@ int main() {
     run<EXACT_DUAL, 6, 16>("exact dual (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
     run<WIDE, 10, 16>("wide pair (cfg3-like)", sms, 49, 0, kPairSpan, 4);
     run<WIDE_EXACT, 10, 16>("wide pair exact (cfg3-like)", sms, 49, 0, kPairSpan, 4);
+    run<K16_DUAL, 10, 8>("k16 2x2 dual (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
+    run<K16_DUAL, 10, 10>("k16 2x2 dual (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
+    run<K16_SINGLE, 9, 10>("k16 2x2 single (cfg1-like)", sms, 14, 0, span1, 2);
+    run<K16_SINGLE, 10, 10>("k16 2x2 single (cfg5-like)", sms, 49, 0, span3, 4);
+    run<K16_SINGLE, 9, 8>("k16 2x2 single (cfg1-like)", sms, 14, 0, span1, 2);
+    run<K16_SINGLE, 10, 8>("k16 2x2 single (cfg5-like)", sms, 49, 0, span3, 4);
     run<WIDE, 9, 16>("wide pair (cfg1-like)", sms, 14, 0, span1, 2);
     run<WIDE_EXACT, 9, 16>("wide pair exact (cfg1-like)", sms, 14, 0, span1, 2);
     run<WIDE, 10, 16>("wide pair (cfg5-like)", sms, 49, 0, span3, 4);
