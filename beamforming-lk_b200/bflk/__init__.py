@@ -29,7 +29,7 @@ SYMBOLS = [
     "bflk_set_geometry", "bflk_set_tiled_geometry", "bflk_get_geometry", "bflk_set_channel_mask",
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_grid_shape", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
-    "bflk_power_map_batch", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
+    "bflk_power_map_batch", "bflk_power_map_batch_submit", "bflk_power_map_batch_wait", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
     "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
@@ -94,6 +94,8 @@ def load_library():
     L.bflk_power_map.argtypes = [vp, vp, vp]
     L.bflk_power_map_i32.argtypes = [vp, vp, vp]
     L.bflk_power_map_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_submit.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_wait.argtypes = [vp]
     L.bflk_power_map_batch_i32.argtypes = [vp, vp, i64, i32, vp]
     L.bflk_power_map_batch_i32_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
@@ -361,6 +363,14 @@ class Beamformer:
     def power_map_batch_ptr(self, stream_ptr, n_samples, n_frames, power_ptr, cuda_stream=0):
         """Raw host-pointer variant (pinned buffers) -- what bench.py's e2e leg calls."""
         self._check(self._L.bflk_power_map_batch(self._h, C.c_void_p(stream_ptr), n_samples, n_frames, C.c_void_p(power_ptr)))
+
+    def power_map_batch_submit_ptr(self, stream_ptr, n_samples, n_frames, power_ptr):
+        """Asynchronous host batch (page-locked buffers): enqueue and return; at most two batches in flight."""
+        self._check(self._L.bflk_power_map_batch_submit(self._h, C.c_void_p(stream_ptr), n_samples, n_frames, C.c_void_p(power_ptr)))
+
+    def power_map_batch_wait(self):
+        """Blocks until the oldest submitted batch has delivered its maps."""
+        self._check(self._L.bflk_power_map_batch_wait(self._h))
 
     def power_map_batch_dev(self, stream_dev_ptr, n_samples, n_frames, power_dev_ptr, cuda_stream=0):
         """Device pointers (e.g. torch tensors' data_ptr()), asynchronous on cuda_stream."""

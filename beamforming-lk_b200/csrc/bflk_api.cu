@@ -93,6 +93,11 @@ int bflk_destroy(bflk_handle *h) {
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
     h->d_trig.release(); h->d_soff.release(); h->d_sfrac.release(); h->d_misc.release();
     h->p_in.release(); h->p_out.release(); h->p_trig.release(); h->p_misc.release(); h->p_stage.release();
+    for (int k = 0; k < 2; k++) {
+        h->d_async_in[k].release();
+        h->d_async_out[k].release();
+        if (h->async_done[k]) cudaEventDestroy(h->async_done[k]);
+    }
     h->d_bytes.release(); h->d_wire.release(); h->d_resident.release(); h->d_miso_out.release(); h->d_miso_partial.release(); h->d_miso_counters.release();
     if (h->caller_event) cudaEventDestroy(h->caller_event);
     delete h;
@@ -794,18 +799,14 @@ int host_chunk_frames(bflk_handle *h, int n_frames, int *chunk_frames_out) {
 
 extern "C" {
 
-int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
-    if (!h) return BFLK_ERR_INVALID;
-    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
-    if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
-    if (n_samples < min_stream_samples(h, n_frames))
-        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
-                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
-    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+// Enqueues one host batch: chunked uploads on the copy stream, pack + delay-and-sum per chunk on the handle's stream, D2H
+// of each chunk's maps.  Does not synchronise.  d_in / d_out: the device buffers of this batch.
+static int host_batch_enqueue(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out,
+                              DevBuf<float> &d_in, DevBuf<float> &d_out, cudaEvent_t reuse_after) {
     const int C = h->cfg.n_channels, N = h->cfg.frame_len;
     const size_t n_in = (size_t)C * n_samples, n_out = (size_t)n_frames * h->dir_count;
-    BFLK_CUDA(h, h->d_window.reserve(n_in));
-    BFLK_CUDA(h, h->d_power.reserve(n_out));
+    BFLK_CUDA(h, d_in.reserve(n_in));
+    BFLK_CUDA(h, d_out.reserve(n_out));
     const int64_t tail = frame_tail_samples(h);
     int chunk_frames = n_frames;
     int rc = host_chunk_frames(h, n_frames, &chunk_frames);
@@ -817,20 +818,20 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
         BFLK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->chunk_events.push_back(e);
     }
+    if (reuse_after) BFLK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, reuse_after, 0));   // the batch that used d_in before is done
     // only the samples a frame can touch travel: [history - largest delay, last frame's last tap] -- a third of the
-    // reference's 1024-sample window for a single frame (the rest of d_window is never read)
+    // reference's 1024-sample window for a single frame (the rest of d_in is never read)
     // (a strided copy out of PAGEABLE memory is staged row by row by the driver and loses more than it saves -- measured
     // cfg3: 289 -> 402 us; pageable single-chunk batches go up as one contiguous copy instead)
     cudaPointerAttributes attr{};
     const bool pageable = cudaPointerGetAttributes(&attr, stream) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
     cudaGetLastError();
     if (pageable && n_chunks == 1) {
-        BFLK_CUDA(h, cudaMemcpyAsync(h->d_window.p, stream, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        rc = power_map_dev(h, h->d_window.p, n_samples, n_samples, n_frames, h->d_power.p, h->stream);
+        if (reuse_after) BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, reuse_after, 0));
+        BFLK_CUDA(h, cudaMemcpyAsync(d_in.p, stream, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        rc = power_map_dev(h, d_in.p, n_samples, n_samples, n_frames, d_out.p, h->stream);
         if (rc) return rc;
-        BFLK_CUDA(h, cudaMemcpyAsync(power_out, h->d_power.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
-        h->last_map_on_device = n_frames == 1;
+        BFLK_CUDA(h, cudaMemcpyAsync(power_out, d_out.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         return BFLK_OK;
     }
     int64_t copied = pageable ? 0 : std::max<int64_t>(0, (int64_t)(h->cfg.history - h->max_delay) & ~(int64_t)3);  // samples per row already "on the device"
@@ -839,20 +840,71 @@ int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples,
         const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
         const int64_t need = k == n_chunks - 1 ? last_needed : std::min<int64_t>(last_needed, (int64_t)(f0 + nf) * N + tail);
         if (need > copied) {
-            BFLK_CUDA(h, cudaMemcpy2DAsync(h->d_window.p + copied, n_samples * sizeof(float), stream + copied,
+            BFLK_CUDA(h, cudaMemcpy2DAsync(d_in.p + copied, n_samples * sizeof(float), stream + copied,
                                            n_samples * sizeof(float), (need - copied) * sizeof(float), C,
                                            cudaMemcpyHostToDevice, h->copy_stream));
             copied = need;
         }
         BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
         BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
-        float *pk = h->d_power.p + (size_t)f0 * h->dir_count;
-        rc = power_map_dev(h, h->d_window.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        float *pk = d_out.p + (size_t)f0 * h->dir_count;
+        rc = power_map_dev(h, d_in.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
         if (rc) return rc;
         BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
                                      cudaMemcpyDeviceToHost, h->stream));
     }
+    return BFLK_OK;
+}
+
+static int host_batch_check(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, const float *power_out) {
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
+    if (!stream || !power_out || n_frames <= 0 || n_samples <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map: null buffer or no frames");
+    if (n_samples < min_stream_samples(h, n_frames))
+        return h->fail(BFLK_ERR_INVALID, "bflk_power_map: %lld samples per channel cannot hold %d frames (need %lld)",
+                       (long long)n_samples, n_frames, (long long)min_stream_samples(h, n_frames));
+    return BFLK_OK;
+}
+
+int bflk_power_map_batch_wait(bflk_handle *h) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (h->async_pending == 0) return BFLK_OK;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int slot = (int)((h->async_seq - h->async_pending) & 1);   // the oldest batch in flight
+    BFLK_CUDA(h, cudaEventSynchronize(h->async_done[slot]));
+    h->async_pending--;
+    return BFLK_OK;
+}
+
+// Asynchronous flavour for continuous operation: returns once the batch is enqueued; at most two batches are in flight
+// (a third submit first waits for the oldest).  The upload of batch i + 1 overlaps the kernels of batch i.
+int bflk_power_map_batch_submit(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    int rc = host_batch_check(h, stream, n_samples, n_frames, power_out);
+    if (rc) return rc;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    while (h->async_pending >= 2)
+        if ((rc = bflk_power_map_batch_wait(h))) return rc;
+    const int slot = (int)(h->async_seq & 1);
+    if (!h->async_done[slot]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->async_done[slot], cudaEventDisableTiming));
+    rc = host_batch_enqueue(h, stream, n_samples, n_frames, power_out, h->d_async_in[slot], h->d_async_out[slot],
+                            h->async_seq >= 2 ? h->async_done[slot] : nullptr);
+    if (rc) return rc;
+    BFLK_CUDA(h, cudaEventRecord(h->async_done[slot], h->stream));
+    h->async_seq++;
+    h->async_pending++;
+    h->last_map_on_device = false;
+    return BFLK_OK;
+}
+
+int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    int rc = host_batch_check(h, stream, n_samples, n_frames, power_out);
+    if (rc) return rc;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    rc = host_batch_enqueue(h, stream, n_samples, n_frames, power_out, h->d_window, h->d_power, nullptr);
+    if (rc) return rc;
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->async_pending = 0;                    // everything queued on the stream before this call has completed too
     h->last_map_on_device = n_frames == 1;   // d_power[0 .. count) is the map: bflk_targets(NULL) / bflk_heatmap(NULL) use it
     return BFLK_OK;
 }

@@ -203,6 +203,11 @@ struct bflk_handle {
     const int32_t *wire_src = nullptr;        // set for the duration of a wire-format call: power_map_dev packs from it
     bflk::DevBuf<int32_t> d_wire;
     bflk::DevBuf<uint8_t> d_bytes;            // heat-map / resize / peak-candidate scratch
+    // bflk_power_map_batch_submit / _wait: two batches in flight, each with its own device buffers
+    bflk::DevBuf<float> d_async_in[2], d_async_out[2];
+    cudaEvent_t async_done[2] = {nullptr, nullptr};
+    uint64_t async_seq = 0;
+    int async_pending = 0;
     bool last_map_on_device = false;          // d_power holds the [count] map of the last single-frame call
     bflk::DevBuf<float> d_resident;
     bflk::DevBuf<float> d_miso_out;           // [flag | audio | power]: one D2H copy per call

@@ -556,17 +556,37 @@ def run_ours(args, c, name):
             def e2e_step():
                 we.power_map_batch_sharded_ptr(host_in.data_ptr(), T, B, out_ptr)
         e2e_steps = max(3, min(args.steps, 40) // 2)
+
+        def wall(fn_all):
+            """ms of fn_all() between barriers, host wall clock, max over ranks (the host API returns after the D2H copy)"""
+            tm.barrier()
+            t0 = time.perf_counter()
+            fn_all()
+            tm.barrier()
+            v = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
+            if world > 1:
+                dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            return float(v.item())
+
         e2e_step()
-        tm.barrier()
-        # synchronous host API (returns after the D2H copy): host wall clock brackets the calls, max over ranks
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        tm.barrier()
-        ems = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        ems = float(ems.item())
+        ems_sync = wall(lambda: [e2e_step() for _ in range(e2e_steps)])
+        ems = ems_sync
+        pipelined = False
+        if world == 1:
+            # continuous operation: bflk_power_map_batch_submit / _wait, two batches in flight -- the upload of step i + 1 runs
+            # under the kernels of step i; every step still uploads its own input and reads back its own maps
+            host_out2 = torch.empty((B, D), dtype=torch.float32).pin_memory()
+            outs = [host_out, host_out2]
+
+            def pipelined_steps():
+                for i in range(e2e_steps):
+                    w.power_map_batch_submit_ptr(host_in.data_ptr(), T, B, outs[i & 1].data_ptr())
+                for _ in range(2):
+                    w.power_map_batch_wait()
+            pipelined_steps()
+            ems = wall(pipelined_steps)
+            pipelined = True
+            assert torch.equal(host_out, host_out2)
         # what the PCIe links deliver when every rank uploads at once (the e2e path moves C*T*4 bytes per step in total)
         probe_bytes = min(host_in.numel() * 4, 64 << 20)
         probe_dev = torch.empty(probe_bytes // 4, dtype=torch.float32, device=dev)
@@ -583,7 +603,8 @@ def run_ours(args, c, name):
         del probe_dev
         e2e = {"value": B * e2e_steps / (ems / 1e3), "unit": UNIT, "h2d_gbs_per_rank_all_ranks_uploading": float(h2d_gbs.item()), "h2d_bytes_per_step": C * T * 4 if world == 1 else
                C * (B * N + gf * (c["W"] - N)) * 4, "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
-               "path": "bflk_power_map_batch (host buffers)" if world == 1 else
+               "synchronous_call_value": B * e2e_steps / (ems_sync / 1e3), "pipelined": pipelined,
+               "path": "bflk_power_map_batch_submit / _wait, two batches in flight (host buffers; synchronous_call_value = bflk_power_map_batch, one call at a time)" if world == 1 else
                "bflk_power_map_batch_sharded: per frame chunk each rank uploads C/G_d channel rows over its own PCIe link, NCCL all-gather "
                "inside the frame group (copy stream) overlapping the kernels of the previous chunk, NCCL all-gather of the maps, D2H of "
                "[B][D] on rank 0; h2d bytes summed over the ranks" + (f"; {we.comm_info()[2]} direction groups x {we.comm_info()[3]} frame groups" if world > 1 else ""),

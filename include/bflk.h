@@ -107,6 +107,12 @@ int bflk_power_map(bflk_handle *h, const float *window, float *power_out);
  * i.e. consecutive frames advance by N samples like Streams::forward().  T >= (B-1)*N + H + N + 1.
  * power_out[B][count]. */
 int bflk_power_map_batch(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* Continuous operation: _submit returns as soon as the batch is enqueued (at most two batches in flight; a third submit
+ * waits for the oldest), _wait blocks until the oldest batch in flight has delivered its maps into the power_out it was
+ * submitted with.  The upload of batch i + 1 overlaps the kernels of batch i.  stream / power_out must stay valid and
+ * untouched until the matching _wait; page-locked buffers (bflk_pin_host) are needed for the copies to overlap. */
+int bflk_power_map_batch_submit(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+int bflk_power_map_batch_wait(bflk_handle *h);
 /* One frame straight from the wire format: frames[W][C] int32, one row per time sample as the FPGA sends it
  * (src/fpga/receiver.h:24-30).  The conversion of Pipeline::receive_exposure (serpentine un-flip, / 2^23,
  * src/fpga/pipeline.cpp:260-297) runs on the device and feeds the power map without a host round trip. */
