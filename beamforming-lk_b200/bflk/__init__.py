@@ -34,7 +34,7 @@ SYMBOLS = [
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
-    "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded",
+    "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded", "bflk_power_map_batch_sharded_submit", "bflk_power_map_batch_sharded_wait",
     "bflk_group_create", "bflk_group_destroy", "bflk_group_size", "bflk_group_handle", "bflk_group_last_error",
     "bflk_group_set_geometry", "bflk_group_set_tiled_geometry", "bflk_group_set_channel_mask", "bflk_group_set_grid_fov",
     "bflk_group_set_kernel", "bflk_group_power_map_batch", "bflk_group_power_map_batch_dev", "bflk_group_synchronize",
@@ -125,6 +125,8 @@ def load_library():
     L.bflk_shard_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.bflk_power_map_batch_sharded_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_power_map_batch_sharded.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_sharded_submit.argtypes = [vp, vp, i64, i32, vp]
+    L.bflk_power_map_batch_sharded_wait.argtypes = [vp]
     L.bflk_group_create.argtypes = [C.POINTER(Config), vp, i32, i32, C.POINTER(vp)]
     L.bflk_group_destroy.argtypes = [vp]
     L.bflk_group_size.argtypes = [vp]
@@ -236,6 +238,13 @@ class Beamformer:
     def power_map_batch_sharded_dev(self, stream_dev_ptr, n_samples, n_frames, power_all_dev_ptr, cuda_stream=0):
         self._check(self._L.bflk_power_map_batch_sharded_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
                                                              C.c_void_p(power_all_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_sharded_submit_ptr(self, stream_ptr, n_samples, n_frames, power_ptr):
+        self._check(self._L.bflk_power_map_batch_sharded_submit(self._h, C.c_void_p(stream_ptr), n_samples, n_frames,
+                                                                C.c_void_p(power_ptr) if power_ptr else None))
+
+    def power_map_batch_sharded_wait(self):
+        self._check(self._L.bflk_power_map_batch_sharded_wait(self._h))
 
     def power_map_batch_sharded_ptr(self, stream_ptr, n_samples, n_frames, power_ptr):
         self._check(self._L.bflk_power_map_batch_sharded(self._h, C.c_void_p(stream_ptr), n_samples, n_frames,

@@ -96,6 +96,9 @@ struct bflk_comm {
     DevBuf<float> d_chunk[kRing];   // [C][Tj] replicated chunk
     DevBuf<int32_t> d_agree;
     cudaEvent_t ev_up[kRing] = {nullptr, nullptr, nullptr}, ev_done[kRing] = {nullptr, nullptr, nullptr};
+    bool ev_done_recorded[kRing] = {false, false, false};
+    cudaEvent_t ev_async = nullptr;   // end of the last submitted (not yet waited for) host batch
+    int async_pending = 0;
     cudaStream_t copy_stream = nullptr;
     int agreed_for_frames = -1, agreed_chunk = 0;   // chunking the ranks of a frame group agreed on
     int64_t collectives = 0;
@@ -303,7 +306,7 @@ int agree_on_chunk(const std::vector<bflk_handle *> &hs, const std::vector<Plan>
 }
 
 int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int64_t n_samples, int32_t n_frames,
-                 const std::vector<float *> &power_out) {
+                 const std::vector<float *> &power_out, bool wait_for_it = true) {
     Nccl &n = nccl();
     const size_t G = hs.size();
     std::vector<Plan> plans(G);
@@ -368,7 +371,9 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             bflk_comm *c = h->comm;
             BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
             const Chunk k = chunk_of(i, j);
-            if (j >= kRing) BFLK_CUDA(h, cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0));
+            // the compute that last used this ring buffer (an earlier chunk of this batch, or of the previous batch when
+            // batches are submitted back to back) must be done before the copy overwrites it
+            if (c->ev_done_recorded[buf]) BFLK_CUDA(h, cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0));
             const bool split = c->gd > 1 && C % c->gd == 0;
             if (split) {
                 const int rows = C / c->gd;
@@ -412,6 +417,7 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_up[buf], 0));
             if ((rc = compute_shard(h, plans[i], c->d_chunk[buf].p, k.pitch, k.Tj, 0, k.nfj, k.a, h->stream))) return rc;
             BFLK_CUDA(h, cudaEventRecord(c->ev_done[buf], h->stream));
+            c->ev_done_recorded[buf] = true;
         }
     }
     std::vector<float *> out_dev(G);
@@ -428,8 +434,16 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             BFLK_CUDA(h, cudaMemcpyAsync(power_out[i], h->comm->d_all.p, (size_t)n_frames * h->n_dir * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     for (size_t i = 0; i < G; i++) {
-        BFLK_CUDA(hs[i], cudaSetDevice(hs[i]->cfg.device));
-        BFLK_CUDA(hs[i], cudaStreamSynchronize(hs[i]->stream));
+        bflk_handle *h = hs[i];
+        BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+        if (wait_for_it) {
+            BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
+            h->comm->async_pending = 0;
+        } else {
+            if (!h->comm->ev_async) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->comm->ev_async, cudaEventDisableTiming));
+            BFLK_CUDA(h, cudaEventRecord(h->comm->ev_async, h->stream));   // everything of this batch precedes it on the stream
+            h->comm->async_pending++;
+        }
     }
     return BFLK_OK;
 }
@@ -491,6 +505,7 @@ void bflk::comm_release(bflk_handle *h) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
     }
+    if (c->ev_async) cudaEventDestroy(c->ev_async);
     for (int k = 0; k < kRing; k++) {
         if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]);
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
@@ -558,6 +573,23 @@ int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, in
 int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
     if (!h) return BFLK_ERR_INVALID;
     return sharded_host({h}, stream, n_samples, n_frames, {power_out});
+}
+
+// Continuous operation: enqueue and return; the stream orders successive batches (the ring buffers of the upload path
+// are guarded by events), so the uploads of batch i + 1 run under the kernels and collectives of batch i.  _wait blocks
+// until everything submitted so far has delivered its maps.  Collective: every rank submits and waits alike.
+int bflk_power_map_batch_sharded_submit(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {
+    if (!h) return BFLK_ERR_INVALID;
+    return sharded_host({h}, stream, n_samples, n_frames, {power_out}, false);
+}
+
+int bflk_power_map_batch_sharded_wait(bflk_handle *h) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!h->comm || h->comm->async_pending == 0) return BFLK_OK;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    BFLK_CUDA(h, cudaEventSynchronize(h->comm->ev_async));
+    h->comm->async_pending = 0;
+    return BFLK_OK;
 }
 
 // ---- one process, several devices -----------------------------------------------------------------------------

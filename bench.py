@@ -587,6 +587,16 @@ def run_ours(args, c, name):
             ems = wall(pipelined_steps)
             pipelined = True
             assert torch.equal(host_out, host_out2)
+        else:
+            def pipelined_steps():
+                for i in range(e2e_steps):
+                    we.power_map_batch_sharded_submit_ptr(host_in.data_ptr(), T, B, out_ptr)
+                    if i & 1:
+                        we.power_map_batch_sharded_wait()      # at most two batches in flight
+                we.power_map_batch_sharded_wait()
+            pipelined_steps()
+            ems = wall(pipelined_steps)
+            pipelined = True
         # what the PCIe links deliver when every rank uploads at once (the e2e path moves C*T*4 bytes per step in total)
         probe_bytes = min(host_in.numel() * 4, 64 << 20)
         probe_dev = torch.empty(probe_bytes // 4, dtype=torch.float32, device=dev)
@@ -605,7 +615,7 @@ def run_ours(args, c, name):
                C * (B * N + gf * (c["W"] - N)) * 4, "d2h_bytes_per_step": B * D * 4, "steps": e2e_steps,
                "synchronous_call_value": B * e2e_steps / (ems_sync / 1e3), "pipelined": pipelined,
                "path": "bflk_power_map_batch_submit / _wait, two batches in flight (host buffers; synchronous_call_value = bflk_power_map_batch, one call at a time)" if world == 1 else
-               "bflk_power_map_batch_sharded: per frame chunk each rank uploads C/G_d channel rows over its own PCIe link, NCCL all-gather "
+               "bflk_power_map_batch_sharded_submit / _wait (two batches in flight; synchronous_call_value = one call at a time): per frame chunk each rank uploads C/G_d channel rows over its own PCIe link, NCCL all-gather "
                "inside the frame group (copy stream) overlapping the kernels of the previous chunk, NCCL all-gather of the maps, D2H of "
                "[B][D] on rank 0; h2d bytes summed over the ranks" + (f"; {we.comm_info()[2]} direction groups x {we.comm_info()[3]} frame groups" if world > 1 else ""),
                "same_maps_as_resident_path": bool(torch.equal(host_out, ref_maps.cpu())) if rank == 0 else None}

@@ -174,6 +174,11 @@ int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, in
  * C / G_d channel rows of its own frame slice; the slice is replicated inside its frame group over NVLink, chunk by
  * chunk, overlapping the kernels.  power_out[B][D] (NULL on ranks that do not need the maps).  Synchronous. */
 int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+/* Continuous operation (every rank alike): _submit enqueues a host batch and returns, _wait blocks until everything
+ * submitted so far has delivered its maps; the uploads of batch i + 1 run under the kernels and collectives of batch i.
+ * stream / power_out must stay valid until the _wait. */
+int bflk_power_map_batch_sharded_submit(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
+int bflk_power_map_batch_sharded_wait(bflk_handle *h);
 /* (b) one process, several devices (single-process callers such as the reference's AWProcessingUnit): n_devices
  *     handles, one per device_ids[i], sharing one job; the setters apply to every member. */
 typedef struct bflk_group bflk_group;
