@@ -71,6 +71,7 @@ int bflk_create(const bflk_config *cfg, bflk_handle **out) {
     h->tuning.tile_pairs = env_int("BFLK_TILE_PAIRS", 0);
     h->tuning.tile_mode = env_int("BFLK_TILE_MODE", -1);
     h->tuning.chunk_mib = env_int("BFLK_CHUNK_MIB", 0);
+    h->tuning.chunk_one_stream = env_int("BFLK_CHUNK_ONE_STREAM", 0);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
         return create_fail(BFLK_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -88,6 +89,11 @@ int bflk_destroy(bflk_handle *h) {
         cudaStreamDestroy(h->stream);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int k = 0; k < 2; k++) {
+        if (h->chunk_stream[k]) { cudaStreamSynchronize(h->chunk_stream[k]); cudaStreamDestroy(h->chunk_stream[k]); }
+        if (h->chunk_join[k]) cudaEventDestroy(h->chunk_join[k]);
+    }
+    h->d_packed_alt.release(); h->d_partial_alt.release();
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     h->d_fir.release(); h->d_xyz.release(); h->d_index.release(); h->d_off.release(); h->d_frac.release(); h->d_tiles.release();
     h->d_tile_dirs.release(); h->d_packed.release(); h->d_bcast_table.release(); h->d_bcast_dirs.release(); h->d_bcast_globals.release(); h->d_window.release(); h->d_power.release(); h->d_audio.release(); h->d_partial.release();
@@ -610,16 +616,20 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
     BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     // the packed rows, partial sums and tables are the handle's: a call on another stream than the previous one waits for it
-    if (h->caller_event && h->last_stream != st) BFLK_CUDA(h, cudaStreamWaitEvent(st, h->caller_event, 0));
+    // (the chunk loop of a host batch orders its two streams and scratch sets itself and leaves the event behind at its end)
+    if (!h->chunk_mode && h->caller_event && h->last_stream != st) BFLK_CUDA(h, cudaStreamWaitEvent(st, h->caller_event, 0));
     struct Mark {   // every exit after this point leaves an event behind on the stream the call used
         bflk_handle *h;
         cudaStream_t st;
         ~Mark() {
+            if (h->chunk_mode) return;
             if (!h->caller_event && cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming) != cudaSuccess) return;
             cudaEventRecord(h->caller_event, st);
             h->last_stream = st;
         }
     } mark{h, st};
+    DevBuf<char> &d_packed = h->scratch_slot ? h->d_packed_alt : h->d_packed;
+    DevBuf<float> &d_partial = h->scratch_slot ? h->d_partial_alt : h->d_partial;
     const int N = h->cfg.frame_len, C = h->cfg.n_channels, usable = (int)h->index.size();
     const float norm = static_cast<float>(N * usable);  // power /= float(N_SAMPLES * count), mimo.cpp:137
     // automatic choice: register-tiled kernel when the grid tiles (2x2 direction tiles with small offset
@@ -644,6 +654,7 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
                 want_warps = ((n_tiles + 7) / 8) * pairs * 20 >= (long long)h->sm_count * 9 ? 8 : 4;
             }
         }
+        if (h->chunk_mode) want_warps = 0;   // the chunk loop built the throughput-shape tables before it queued anything
         int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, want_warps);
         if (rc) return rc;
         tiled = h->tiles_usable && (wire || (!(row_stride & 1) && !((uintptr_t)stream_dev & 7)));  // packed rows: 8-byte loads
@@ -682,12 +693,12 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
         a.geom = h->bcast_geom;
         a.power = power_dev;
         a.norm = norm;
-        BFLK_CUDA(h, h->d_packed.reserve(das_bcast_packed_bytes(a)));
-        a.packed = h->d_packed.p;
+        BFLK_CUDA(h, d_packed.reserve(das_bcast_packed_bytes(a)));
+        a.packed = d_packed.p;
         const int nblk = N <= 256 ? 1 : (N - 2 + 253) / 254;
         if (nblk > 1) {
-            BFLK_CUDA(h, h->d_partial.reserve((size_t)n_frames * nblk * h->dir_count));
-            a.partial = h->d_partial.p;
+            BFLK_CUDA(h, d_partial.reserve((size_t)n_frames * nblk * h->dir_count));
+            a.partial = d_partial.p;
         }
         int launches = 0;
         BFLK_CUDA(h, launch_das_bcast(a, st, &launches, timing_hook, h));
@@ -714,12 +725,12 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
         a.geom = h->tile_geom;
         a.power = power_dev;
         a.norm = norm;
-        BFLK_CUDA(h, h->d_packed.reserve(das_tile_packed_bytes(a)));
-        a.packed = h->d_packed.p;
+        BFLK_CUDA(h, d_packed.reserve(das_tile_packed_bytes(a)));
+        a.packed = d_packed.p;
         const int blocks_per_frame = N <= 256 ? 1 : (N - 2 + 253) / 254;
         if (blocks_per_frame > 1) {
-            BFLK_CUDA(h, h->d_partial.reserve((size_t)n_frames * blocks_per_frame * h->dir_count));
-            a.partial = h->d_partial.p;
+            BFLK_CUDA(h, d_partial.reserve((size_t)n_frames * blocks_per_frame * h->dir_count));
+            a.partial = d_partial.p;
         }
         int launches = 0;
         BFLK_CUDA(h, launch_das_tile(a, h->sm_count, st, &launches, timing_hook, h));
@@ -836,6 +847,33 @@ static int host_batch_enqueue(bflk_handle *h, const float *stream, int64_t n_sam
     }
     int64_t copied = pageable ? 0 : std::max<int64_t>(0, (int64_t)(h->cfg.history - h->max_delay) & ~(int64_t)3);  // samples per row already "on the device"
     const int64_t last_needed = std::min<int64_t>(n_samples, (int64_t)(n_frames - 1) * N + tail + N);
+    // several chunks: their kernels alternate between two compute streams (each with its own scratch), so the CTAs of
+    // chunk k + 1 fill the SMs that the last CTAs of chunk k leave idle one by one.  Ordering: a stream's chunks follow
+    // each other; both streams wait for whatever the handle's stream had queued before this batch (tables, a previous
+    // synchronous call) and for the batch that used these device buffers before (reuse_after); at the end the handle's
+    // stream waits for both, so everything ordered after it (async_done, later calls) sees the whole batch.
+    const bool two_streams = n_chunks > 1 && !h->tuning.chunk_one_stream;
+    if (two_streams) {
+        for (int i = 0; i < 2; i++) {
+            if (!h->chunk_stream[i]) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking));
+            if (!h->chunk_join[i]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->chunk_join[i], cudaEventDisableTiming));
+        }
+        // tables first (ensure_tiles synchronises the handle's stream when it has to build them), before any chunk is queued
+        if (!h->fir_phases && (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4)) {
+            rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, 0);
+            if (rc) return rc;
+        }
+        if (h->caller_event)
+            for (int i = 0; i < 2; i++) BFLK_CUDA(h, cudaStreamWaitEvent(h->chunk_stream[i], h->caller_event, 0));
+        if (reuse_after)
+            for (int i = 0; i < 2; i++) BFLK_CUDA(h, cudaStreamWaitEvent(h->chunk_stream[i], reuse_after, 0));
+    }
+    struct ChunkMode {   // power_map_dev leaves the stream ordering to this loop while it runs
+        bflk_handle *h;
+        bool on;
+        ~ChunkMode() { if (on) { h->chunk_mode = false; h->scratch_slot = 0; } }
+    } mode{h, two_streams};
+    h->chunk_mode = two_streams;
     for (int k = 0; k < n_chunks; k++) {
         const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
         const int64_t need = k == n_chunks - 1 ? last_needed : std::min<int64_t>(last_needed, (int64_t)(f0 + nf) * N + tail);
@@ -845,13 +883,24 @@ static int host_batch_enqueue(bflk_handle *h, const float *stream, int64_t n_sam
                                            cudaMemcpyHostToDevice, h->copy_stream));
             copied = need;
         }
+        cudaStream_t cs = two_streams ? h->chunk_stream[k & 1] : h->stream;
+        h->scratch_slot = two_streams ? (k & 1) : 0;
         BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
-        BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
+        BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->chunk_events[k], 0));
         float *pk = d_out.p + (size_t)f0 * h->dir_count;
-        rc = power_map_dev(h, d_in.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        rc = power_map_dev(h, d_in.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, cs);
         if (rc) return rc;
         BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
-                                     cudaMemcpyDeviceToHost, h->stream));
+                                     cudaMemcpyDeviceToHost, cs));
+    }
+    if (two_streams) {
+        for (int i = 0; i < 2; i++) {
+            BFLK_CUDA(h, cudaEventRecord(h->chunk_join[i], h->chunk_stream[i]));
+            BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_join[i], 0));
+        }
+        if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+        BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
+        h->last_stream = h->stream;
     }
     return BFLK_OK;
 }

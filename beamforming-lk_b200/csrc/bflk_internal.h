@@ -72,6 +72,7 @@ struct Tuning {
     int tile_pairs = 0;      // BFLK_TILE_PAIRS: block pairs per CTA
     int tile_mode = -1;      // BFLK_TILE_MODE: 0 one window per 2x2 tile, 1 / 2 one window per direction pair
     int chunk_mib = 0;       // BFLK_CHUNK_MIB: host batches are uploaded in chunks of about this size
+    int chunk_one_stream = 0;  // BFLK_CHUNK_ONE_STREAM=1: the chunks' kernels on one stream (round-2 behaviour, for comparison)
 };
 
 // Shape of the packed rows the tiled kernel stages (das_tile.cu).
@@ -230,6 +231,15 @@ struct bflk_handle {
     // host-buffer batches are cut into chunks: copies on copy_stream overlap compute on stream
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    // ... and the chunks' kernels alternate between two compute streams, each with its own packed-row / partial-sum
+    // scratch: a launch on its own ends with half a CTA lifetime of idle SMs on average (the CTAs of a launch all take
+    // equally long and the SMs drift apart), which the next chunk's CTAs fill when they do not have to wait for it
+    cudaStream_t chunk_stream[2] = {nullptr, nullptr};
+    cudaEvent_t chunk_join[2] = {nullptr, nullptr};
+    bflk::DevBuf<char> d_packed_alt;
+    bflk::DevBuf<float> d_partial_alt;
+    int scratch_slot = 0;         // which scratch set power_map_dev uses (1 only inside a chunked host batch)
+    bool chunk_mode = false;      // power_map_dev is being called by the chunk loop, which orders the streams itself
 
     // optional kernel timing (bflk_enable_timing): event pairs recorded on the launching stream
     bool timing = false;

@@ -42,6 +42,8 @@ PIPE_MODE = os.environ.get("BFLK_GEN_PIPE", "single")
 SHARED_TAIL = os.environ.get("BFLK_GEN_SHARED_TAIL", "0")
 # wide flavour (gen_wide): next channel's window loads from inside the last body (same idea as PIPE_MODE)
 PIPE_MODE_WIDE = os.environ.get("BFLK_GEN_PIPE_WIDE", "0")
+# two-window two-FMA flavour: no join point after the window-B block (measured: see profiles/README.md)
+NOJOIN = os.environ.get("BFLK_GEN_NOJOIN", "0") == "1"
 
 # operand numbers of the asm block: acc[4][8] "+l" 0..31, e0 32, e1 33 ("+r"), f0..f3 34..37 ("+f"),
 # row 38 ("r": shared address of this lane's row start), nxt 39 ("r": shared address of the next entry)
@@ -507,7 +509,14 @@ def gen_fast(nch, dual=False):
                     emit(f"    and.b32 x, dl, {1 << 28};")
                     emit("    setp.ne.b32 q, x, 0;")
                 body(r, dd)
-                if dual:
+                if dual and NOJOIN:
+                    # no join point after the window-B block: the same-window path gets its own copy of the next
+                    # dispatch (out of line, SWS_dd), so ptxas sees no if-then to wrap in BSSY / BSYNC
+                    emit(f"    @q bra.uni SWS_{dd};")
+                    for c in range(4):
+                        emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
+                    window("ob")
+                elif dual:
                     # address adds inside the skipped block: ten instructions are too many for ptxas to if-convert, so a
                     # tile that fits window A really branches around them instead of issuing six predicated-off loads
                     emit(f"    @q bra.uni SW_{dd};")
@@ -548,6 +557,11 @@ def gen_fast(nch, dual=False):
         entry_tail()
         emit("    @ploop bra.uni TOP;")
         emit("    bra.uni DONE;")
+    if dual and NOJOIN:
+        for dd in range(kmax + 1):
+            emit(f"SWS_{dd}:")
+            tree_from(2, dd)
+            emit(f"    bra.uni B2_{dd};")
     for (r, base, b) in sorted(need):
         emit(f"S{r}_{base}_{b}:")
         subtree(r, base, b - 1, f"{r}_{base}_{b}")
