@@ -996,6 +996,28 @@ int bflk_power_map_batch_i32(bflk_handle *h, const int32_t *frames, int64_t n_sa
         h->chunk_events.push_back(e);
     }
     int64_t copied = 0;  // samples (rows) already on the device
+    // chunks alternate between two compute streams like host_batch_enqueue's -- when the register-tiled kernel takes the
+    // wire samples directly (the other kernels go through the handle's one float window, ingest_kernel)
+    bool two_streams = n_chunks > 1 && !h->tuning.chunk_one_stream && !h->fir_phases &&
+                       (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4);
+    if (two_streams) {
+        rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, 0);
+        if (rc) return rc;
+        two_streams = h->tiles_usable;
+    }
+    if (two_streams) {
+        for (int i = 0; i < 2; i++) {
+            if (!h->chunk_stream[i]) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking));
+            if (!h->chunk_join[i]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->chunk_join[i], cudaEventDisableTiming));
+            if (h->caller_event) BFLK_CUDA(h, cudaStreamWaitEvent(h->chunk_stream[i], h->caller_event, 0));
+        }
+    }
+    struct ChunkMode {
+        bflk_handle *h;
+        bool on;
+        ~ChunkMode() { if (on) { h->chunk_mode = false; h->scratch_slot = 0; } }
+    } mode{h, two_streams};
+    h->chunk_mode = two_streams;
     for (int k = 0; k < n_chunks; k++) {
         const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
         const int64_t need = std::min<int64_t>(n_samples, k == n_chunks - 1 ? n_samples : (int64_t)(f0 + nf) * N + tail);
@@ -1004,13 +1026,24 @@ int bflk_power_map_batch_i32(bflk_handle *h, const int32_t *frames, int64_t n_sa
                                          cudaMemcpyHostToDevice, h->copy_stream));
             copied = need;
         }
+        cudaStream_t cs = two_streams ? h->chunk_stream[k & 1] : h->stream;
+        h->scratch_slot = two_streams ? (k & 1) : 0;
         BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
-        BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_events[k], 0));
+        BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->chunk_events[k], 0));
         float *pk = h->d_power.p + (size_t)f0 * h->dir_count;
-        rc = bflk_power_map_batch_i32_dev(h, h->d_wire.p + (size_t)f0 * N * C, copied - (int64_t)f0 * N, nf, pk, h->stream);
+        rc = bflk_power_map_batch_i32_dev(h, h->d_wire.p + (size_t)f0 * N * C, copied - (int64_t)f0 * N, nf, pk, cs);
         if (rc) return rc;
         BFLK_CUDA(h, cudaMemcpyAsync(power_out + (size_t)f0 * h->dir_count, pk, (size_t)nf * h->dir_count * sizeof(float),
-                                     cudaMemcpyDeviceToHost, h->stream));
+                                     cudaMemcpyDeviceToHost, cs));
+    }
+    if (two_streams) {
+        for (int i = 0; i < 2; i++) {
+            BFLK_CUDA(h, cudaEventRecord(h->chunk_join[i], h->chunk_stream[i]));
+            BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_join[i], 0));
+        }
+        if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+        BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
+        h->last_stream = h->stream;
     }
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     return BFLK_OK;

@@ -98,6 +98,7 @@ struct bflk_comm {
     cudaEvent_t ev_up[kRing] = {nullptr, nullptr, nullptr}, ev_done[kRing] = {nullptr, nullptr, nullptr};
     bool ev_done_recorded[kRing] = {false, false, false};
     cudaEvent_t ev_async = nullptr;   // end of the last submitted (not yet waited for) host batch
+    cudaEvent_t ev_fork = nullptr;    // start of a host batch on the handle's stream: its two chunk streams wait for it
     int async_pending = 0;
     cudaStream_t copy_stream = nullptr;
     int agreed_for_frames = -1, agreed_chunk = 0;   // chunking the ranks of a frame group agreed on
@@ -362,6 +363,31 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             if (split) BFLK_CUDA(hs[i], c->d_slice[k].reserve((size_t)(C / c->gd) * Tj));
         }
     }
+    // the chunks' kernels alternate between the handle's two chunk streams (own scratch each, bflk_api.cu host_batch_enqueue):
+    // the CTAs of chunk j + 1 fill the SMs that the last CTAs of chunk j leave idle one by one.  Both streams start after
+    // whatever the handle's stream has queued (the previous batch's all-gather reads the buffers this batch writes).
+    std::vector<char> two_streams(G, 0);
+    for (size_t i = 0; i < G; i++) {
+        bflk_handle *h = hs[i];
+        two_streams[i] = n_chunks[i] > 1 && !h->tuning.chunk_one_stream;
+        if (!two_streams[i]) continue;
+        BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+        if (!h->fir_phases && (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4)) {
+            if ((rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, 0))) return rc;   // before anything is queued on the chunk streams
+        }
+        if (!h->comm->ev_fork) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->comm->ev_fork, cudaEventDisableTiming));
+        BFLK_CUDA(h, cudaEventRecord(h->comm->ev_fork, h->stream));
+        for (int k = 0; k < 2; k++) {
+            if (!h->chunk_stream[k]) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[k], cudaStreamNonBlocking));
+            if (!h->chunk_join[k]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->chunk_join[k], cudaEventDisableTiming));
+            BFLK_CUDA(h, cudaStreamWaitEvent(h->chunk_stream[k], h->comm->ev_fork, 0));
+            if (h->caller_event) BFLK_CUDA(h, cudaStreamWaitEvent(h->chunk_stream[k], h->caller_event, 0));
+        }
+    }
+    struct ChunkMode {   // power_map_dev leaves the stream ordering to this loop while it runs
+        const std::vector<bflk_handle *> &hs;
+        ~ChunkMode() { for (bflk_handle *h : hs) { h->chunk_mode = false; h->scratch_slot = 0; } }
+    } mode{hs};
     for (int j = 0; j < max_chunks; j++) {
         const int buf = j % kRing;
         // upload this chunk's rows (copy stream), after the compute that last used the buffer
@@ -413,12 +439,30 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             bflk_comm *c = h->comm;
             BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
             const Chunk k = chunk_of(i, j);
+            cudaStream_t cs = two_streams[i] ? h->chunk_stream[j & 1] : h->stream;
+            h->chunk_mode = two_streams[i];
+            h->scratch_slot = two_streams[i] ? (j & 1) : 0;
             BFLK_CUDA(h, cudaEventRecord(c->ev_up[buf], c->copy_stream));
-            BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_up[buf], 0));
-            if ((rc = compute_shard(h, plans[i], c->d_chunk[buf].p, k.pitch, k.Tj, 0, k.nfj, k.a, h->stream))) return rc;
-            BFLK_CUDA(h, cudaEventRecord(c->ev_done[buf], h->stream));
+            BFLK_CUDA(h, cudaStreamWaitEvent(cs, c->ev_up[buf], 0));
+            rc = compute_shard(h, plans[i], c->d_chunk[buf].p, k.pitch, k.Tj, 0, k.nfj, k.a, cs);
+            h->chunk_mode = false;
+            h->scratch_slot = 0;
+            if (rc) return rc;
+            BFLK_CUDA(h, cudaEventRecord(c->ev_done[buf], cs));
             c->ev_done_recorded[buf] = true;
         }
+    }
+    for (size_t i = 0; i < G; i++) {
+        bflk_handle *h = hs[i];
+        if (!two_streams[i]) continue;
+        BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+        for (int k = 0; k < 2; k++) {   // the all-gather on the handle's stream follows every chunk
+            BFLK_CUDA(h, cudaEventRecord(h->chunk_join[k], h->chunk_stream[k]));
+            BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_join[k], 0));
+        }
+        if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+        BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
+        h->last_stream = h->stream;
     }
     std::vector<float *> out_dev(G);
     std::vector<cudaStream_t> st(G);
@@ -506,6 +550,7 @@ void bflk::comm_release(bflk_handle *h) {
         cudaStreamDestroy(c->copy_stream);
     }
     if (c->ev_async) cudaEventDestroy(c->ev_async);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < kRing; k++) {
         if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]);
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);

@@ -549,6 +549,23 @@ def test_chunked_host_batch_equals_small_batches(bf):
         assert np.array_equal(full[b0:b0 + nb], part)
 
 
+def test_chunked_wire_batch_equals_float_path(bf, oracle):
+    """A wire batch big enough to travel in several chunks (their kernels alternate between two compute streams, each with
+    its own packed-row scratch): same bits as the float path, pinned and pageable buffers, repeated calls."""
+    from bflk import synth
+    w = bf.MIMOWorker(cases.origins(1, 1), 8, 8, 180.0)
+    B = 2600                                               # 64 channels x 2600 frames x 4 B = 170 MB -> several chunks
+    base = synth.make_stream(synth.tile_geometry(cases.origins(1, 1)), 40 * 256 + 1024)
+    stream = np.ascontiguousarray(np.tile(base[:, :40 * 256], (1, B // 40 + 2))[:, :(B - 1) * 256 + 1024])
+    stream *= np.linspace(0.5, 1.5, stream.shape[1], dtype=np.float32)[None, :]
+    wire = synth.to_wire_i32(stream)
+    exposure = oracle.ingest(wire)
+    ref = w.power_map_batch(exposure, B)
+    for _ in range(2):
+        assert np.array_equal(w.power_map_batch_i32(wire, B), ref)
+    assert np.array_equal(w.power_map_batch(exposure, B), ref)
+
+
 def test_submit_wait_pipeline_equals_synchronous_calls(bf):
     """Continuous operation: batches submitted back to back (two in flight) deliver the same bits as synchronous calls,
     in order, into the buffers they were submitted with; mixing in a synchronous call drains the pipeline."""
