@@ -344,8 +344,9 @@ int das_tile_max_span() { return 11; }
 size_t das_tile_entry_bytes(const TileGeometry &g);
 
 size_t das_tile_smem_bytes(const TileGeometry &g, int stages) {
-    // + 96: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used)
-    return (size_t)stages * (kCC * g.row_bytes + g.warps * kCC * das_tile_entry_bytes(g)) + stages * (8 + 4) + 96;
+    // + 256: the fast variant's entry prefetch reads one entry past the last stage buffer's table (never used), and a window
+    // whose last chunk no direction reads loads that chunk from [entry pointer + up to 192] instead (one broadcast wavefront)
+    return (size_t)stages * (kCC * g.row_bytes + g.warps * kCC * das_tile_entry_bytes(g)) + stages * (8 + 4) + 256;
 }
 
 TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_tiles, int mode, int fast, const Tuning *tuning, int want_warps) {

@@ -124,7 +124,7 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
             o[slot] = off[(size_t)g * C + c];
             e.frac[slot] = frac[(size_t)g * C + c];
         }
-        unsigned packed = 0;
+        unsigned packed = 0, need_last = 0;   // need_last: bit 29 / 30 = window A / B has a delta that reaches the last chunk
         int span = 0;
         if (mode == 0) {
             // window = smallest offset of the tile, exactly: an odd start reads the copy shifted by one sample pair
@@ -139,6 +139,7 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                 span = max(span, dlt);
                 packed |= (unsigned)(dlt & 63) << (6 * slot);
             }
+            if (span >= pair_span - 1) need_last = 1u << 29;
         } else {
             // one window per direction pair -- unless the whole tile fits a pair window for this channel: then slots 2,3
             // reuse window A (bit 28; the kernel skips the second load + differences)
@@ -157,6 +158,8 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                     const int dlt = o[2 * w + k] - base;
                     span = max(span, dlt);
                     packed |= (unsigned)(dlt & 63) << (6 * (2 * w + k));
+                    // (a tile that fits window A: all four deltas are relative to it)
+                    if (dlt >= pair_span - 1) need_last |= 1u << (same ? 29 : 29 + w);
                 }
             }
             if (same) packed |= 1u << 28;
@@ -173,7 +176,7 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 q.cls_off[k] = (unsigned)(s % kTileCC) * 2u * (unsigned)copy_bytes + e.win_off + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
-            q.deltas = packed & 0xffffffu;
+            q.deltas = (packed & 0xffffffu) | need_last;
             q.span = span;
             q.reserved[0] = q.reserved[1] = 0;
 #pragma unroll
@@ -192,7 +195,7 @@ __global__ void build_tiles_kernel(const int32_t *__restrict__ off, const float 
                 for (int k = 0; k < 4; k++)
                     (w ? q.cls_b : q.cls_a)[k] = (unsigned)(s % kTileCC) * 2u * (unsigned)copy_bytes + wo + ((k > 0 && r >= (unsigned)(4 - k)) ? 16u : 0u);
             }
-            q.deltas = packed & 0x10ffffffu;
+            q.deltas = (packed & 0x10ffffffu) | need_last;
             q.span = span;
             q.reserved[0] = q.reserved[1] = 0;
 #pragma unroll

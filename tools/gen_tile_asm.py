@@ -44,6 +44,16 @@ SHARED_TAIL = os.environ.get("BFLK_GEN_SHARED_TAIL", "0")
 PIPE_MODE_WIDE = os.environ.get("BFLK_GEN_PIPE_WIDE", "0")
 # two-window two-FMA flavour: no join point after the window-B block (measured: see profiles/README.md)
 NOJOIN = os.environ.get("BFLK_GEN_NOJOIN", "0") == "1"
+# two-FMA variants: fetch the last window chunk (4 of 24 shared-memory wavefronts) only where the table says a direction
+# reads it (bits 29 / 30 of the delta word; cfg3: 33.5 instead of 36 window wavefronts per (warp, channel), cfg5: 20 instead
+# of 24).  ADAPT_MODE pred = predicated LDS (ptxas keeps the chunk's old registers alive and moves accumulators around the
+# window-B block: 135 instead of 82 MOVs), sel = always load, from a warp-uniform address (one broadcast wavefront) when not
+# needed (+1 LOP3 +1 SEL per window).  Measured on one B200, same box, sel mode vs off: cfg3 0.5794 vs 0.5768, cfg2 0.6210 vs
+# 0.6225, cfg1 0.6485 vs 0.6501, cfg5 0.6046 vs 0.6051 -- the wavefronts saved are worth no more than the two instructions
+# added (the loop is bound by issue slots, not by shared-memory wavefronts) -> off
+ADAPT = os.environ.get("BFLK_GEN_ADAPT", "0") == "1"
+ADAPT_MODE = os.environ.get("BFLK_GEN_ADAPT_MODE", "sel")
+ADAPT_PWB_EARLY = os.environ.get("BFLK_GEN_ADAPT_PWB_EARLY", "0") == "1"
 
 # operand numbers of the asm block: acc[4][8] "+l" 0..31, e0 32, e1 33 ("+r"), f0..f3 34..37 ("+f"),
 # row 38 ("r": shared address of this lane's row start), nxt 39 ("r": shared address of the next entry)
@@ -377,6 +387,9 @@ def gen_fast(nch, dual=False):
     o_dl, o_f, o_g = (64, 32, 48) if dual else (16, 32, 48)
     shared_tail = SHARED_TAIL == "1" or (SHARED_TAIL == "dual" and dual)
     PIPE = PIPE_MODE == "1" or (PIPE_MODE == "single" and not dual)
+    # the last window chunk is loaded only for the (window, channel)s whose largest delta reaches it (kmax - 1 or more):
+    # a predicated-off LDS still issues but moves no shared-memory wavefronts.  nch = 5 always needs its last chunk.
+    adapt = ADAPT and kmax >= 2
     L = []
     emit = L.append
 
@@ -397,7 +410,21 @@ def gen_fast(nch, dual=False):
         if os.environ.get("BFLK_GEN_EXP") == "nolds" and not first_window[0]:
             return      # timing experiment only (wrong results): how much do the window loads cost?
         for m in range(nch):
-            emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [{o}{m & 3}+{16 * (m + (m >> 2))}];")
+            # the last chunk (pairs 2 nch - 2, 2 nch - 1) is read only by bodies with delta >= kmax - 1: the table says per
+            # (window, channel) whether any direction needs it (bit 29 window A, bit 30 window B of the delta word)
+            if adapt and m == nch - 1 and ADAPT_MODE == "sel":
+                # (a full definition of the chunk's registers: a predicated load would keep their old values alive and
+                # ptxas then moves accumulators around the window-B block -- 135 instead of 82 MOVs in the dual kernel)
+                emit(f"    selp.u32 xl, {o}{m & 3}, {ENT}, pw{o[1]};")
+                emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [xl+{16 * (m + (m >> 2))}];")
+                continue
+            pred = f"@pw{o[1]} " if adapt and m == nch - 1 else ""
+            emit(f"    {pred}ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [{o}{m & 3}+{16 * (m + (m >> 2))}];")
+
+    def need_last(w, extra=""):
+        """pw{w} = the window's last chunk is needed (and `extra`, a predicate)"""
+        emit(f"    and.b32 x, dl, {1 << (29 if w == 'a' else 30)};")
+        emit(f"    setp.ne{'.and' if extra else ''}.b32 pw{w}, x, 0{', ' + extra if extra else ''};")
 
     def load_entry_head():
         emit(f"    ld.shared.v4.u32 {{oa0, oa1, oa2, oa3}}, [{ENT}];")
@@ -416,6 +443,8 @@ def gen_fast(nch, dual=False):
         if prologue[0] or not PIPE:
             for c in range(4):
                 emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+            if adapt:
+                need_last("a")
         prologue[0] = False
         preds(0)
 
@@ -447,8 +476,8 @@ def gen_fast(nch, dual=False):
             emit(f"    @{'!' if want else ''}p{b} bra.uni S{r}_{base}_{b};")
 
     emit("{")
-    emit(f"    .reg .pred p<{nbits}>, ploop, q;")
-    emit("    .reg .b32 x, dl, oa<4>, ob<4>;")
+    emit(f"    .reg .pred p<{nbits}>, ploop, q, pwa, pwb;")
+    emit("    .reg .b32 x, xl, dl, oa<4>, ob<4>;")
     emit("    .reg .f32 f<4>, g<4>;")
     emit(f"    .reg .b64 ff<4>, gg<4>, w<{nw}>;")
     load_entry_head()
@@ -488,7 +517,11 @@ def gen_fast(nch, dual=False):
                     continue
                 if all(last_use.get(j, -1) <= pos for j in (2 * m, 2 * m + 1)):
                     loaded.add(m)
-                    emit(f"    @ploop ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [oa{m & 3}+{16 * (m + (m >> 2))}];")
+                    if adapt and m == nch - 1 and ADAPT_MODE == "sel":
+                        emit(f"    @ploop ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [xl+{16 * (m + (m >> 2))}];")
+                        continue
+                    pred = "pwa" if adapt and m == nch - 1 else "ploop"
+                    emit(f"    @{pred} ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [oa{m & 3}+{16 * (m + (m >> 2))}];")
 
         issue_free(-1)
         for pos, (kind, k) in enumerate(order):
@@ -508,6 +541,8 @@ def gen_fast(nch, dual=False):
                 if dual:
                     emit(f"    and.b32 x, dl, {1 << 28};")
                     emit("    setp.ne.b32 q, x, 0;")
+                    if adapt and ADAPT_PWB_EARLY:
+                        need_last("b")
                 body(r, dd)
                 if dual and NOJOIN:
                     # no join point after the window-B block: the same-window path gets its own copy of the next
@@ -515,6 +550,8 @@ def gen_fast(nch, dual=False):
                     emit(f"    @q bra.uni SWS_{dd};")
                     for c in range(4):
                         emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
+                    if adapt:
+                        need_last("b")
                     window("ob")
                 elif dual:
                     # address adds inside the skipped block: ten instructions are too many for ptxas to if-convert, so a
@@ -522,6 +559,8 @@ def gen_fast(nch, dual=False):
                     emit(f"    @q bra.uni SW_{dd};")
                     for c in range(4):
                         emit(f"    add.u32 ob{c}, ob{c}, {ROWR};")
+                    if adapt and not ADAPT_PWB_EARLY:
+                        need_last("b")
                     window("ob")
                     emit(f"SW_{dd}:")
                 tree_from(2, dd)
@@ -538,6 +577,11 @@ def gen_fast(nch, dual=False):
                 if PIPE:
                     for c in range(4):
                         emit(f"    add.u32 oa{c}, oa{c}, {ROWR};")
+                    if adapt and ADAPT_MODE == "sel":
+                        need_last("a")
+                        emit(f"    selp.u32 xl, oa{(nch - 1) & 3}, {ENT}, pwa;")
+                    elif adapt:
+                        need_last("a", "ploop")
                     body_recycling(r, dd)
                 else:
                     emit(f"    add.u32 {ENT}, {ENT}, {esz};")

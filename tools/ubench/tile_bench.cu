@@ -165,6 +165,7 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
                     const int zero_slot = rng() & 3;
                     for (int k = 0; k < 4; k++) dl |= (uint32_t)(k == zero_slot ? 0 : (sp ? rng() % (sp + 1) : 0)) << (6 * k);
                     if (sp) dl = (dl & ~(63u << (6 * ((zero_slot + 1) & 3)))) | ((uint32_t)sp << (6 * ((zero_slot + 1) & 3)));
+                    if (sp >= 2 * NCH - 10) dl |= 1u << 29;   // a delta reaches the window's last chunk
                     float g[4];
                     for (int k = 0; k < 4; k++) g[k] = 1.0f - fr[k];
                     memcpy(e, o, 16); memcpy(e + 16, &dl, 4); memcpy(e + 32, fr, 16); memcpy(e + 48, g, 16);
@@ -176,8 +177,12 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
                         for (int k = 0; k < 4; k++) (w2 ? ob : oa)[k] = c * row_bytes + odd * copy_bytes + 16 * padded4(q) + ((k > 0 && r >= 4 - k) ? 16 : 0);
                         const int sp = pick_span();
                         dl |= ((rng() & 1) ? (uint32_t)sp : ((uint32_t)sp << 6)) << (12 * w2);
+                        if (sp >= 2 * NCH - 10) dl |= 1u << (29 + w2);
                     }
-                    if (std::uniform_real_distribution<double>(0, 1)(rng) < same_window_share) dl |= 1u << 28;
+                    if (std::uniform_real_distribution<double>(0, 1)(rng) < same_window_share) {
+                        dl |= 1u << 28;
+                        if (dl & (1u << 30)) dl = (dl & ~(1u << 30)) | (1u << 29);   // all four deltas refer to window A
+                    }
                     float g[4];
                     for (int k = 0; k < 4; k++) g[k] = 1.0f - fr[k];
                     memcpy(e, oa, 16); memcpy(e + 16, ob, 16); memcpy(e + 32, fr, 16); memcpy(e + 48, g, 16); memcpy(e + 64, &dl, 4);
@@ -224,7 +229,8 @@ int main() {
     (void)span2; (void)kTileSpanFine;
     // fine grids (cfg1 / cfg5): one window per 2x2 tile
     run<FAST_SINGLE, 5, 16>("fast single (cfg1-like)", sms, 14, 0, span1, 2);
-    run<FAST_SINGLE, 6, 16>("fast single (cfg5-like)", sms, 49, 0, span3, 4);
+    run<FAST_SINGLE, 6, 16>("fast single (span 0..3)", sms, 49, 0, span3, 4);
+    run<FAST_SINGLE, 6, 16>("fast single (cfg5 spans)", sms, 49, 0, span2, 3);
     run<EXACT_SINGLE, 5, 16>("exact single (cfg1-like)", sms, 14, 0, span1, 2);
     run<EXACT_SINGLE, 6, 16>("exact single (cfg5-like)", sms, 49, 0, span3, 4);
     // coarse grid (cfg3): two windows per 2x2 tile today vs one direction pair x 16 sample pairs per lane
