@@ -70,6 +70,9 @@ int bflk_create(const bflk_config *cfg, bflk_handle **out) {
     h->tuning.tile_stages = env_int("BFLK_TILE_STAGES", 0);
     h->tuning.tile_pairs = env_int("BFLK_TILE_PAIRS", 0);
     h->tuning.tile_mode = env_int("BFLK_TILE_MODE", -1);
+    h->tuning.no_ksplit = env_int("BFLK_NO_KSPLIT", 0);
+    h->tuning.lat_warps = env_int("BFLK_LAT_WARPS", 0);
+    h->tuning.lat_split = env_int("BFLK_LAT_SPLIT", 0);
     h->tuning.chunk_mib = env_int("BFLK_CHUNK_MIB", 0);
     h->tuning.chunk_one_stream = env_int("BFLK_CHUNK_ONE_STREAM", 0);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -387,6 +390,12 @@ int bflk_set_kernel(bflk_handle *h, int32_t which) {
     return BFLK_OK;
 }
 
+int bflk_set_channel_split(bflk_handle *h, int32_t on) {
+    if (!h) return BFLK_ERR_INVALID;
+    h->allow_ksplit = on != 0;
+    return BFLK_OK;
+}
+
 int64_t bflk_launch_count(const bflk_handle *h) { return h ? h->launches : 0; }
 
 int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks) {
@@ -604,6 +613,36 @@ static int ensure_bcast(bflk_handle *h) {
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold row_len valid samples
 }  // extern "C"
 
+// CTA shape of a call that cannot fill two waves of 16-warp CTAs (a live worker's single frame).  One CTA per SM (the stage
+// ring takes the shared memory), so the call takes waves x the time of one CTA = a fixed cost (launch, barrier set-up, first
+// bulk copies, epilogue) + its channels x the time of a channel step, which depends on the warps that share a scheduler.
+// The two-FMA variants can also split the channels of a block pair across a thread-block cluster of 2 or 4 CTAs (das_tile.cu,
+// KSPLIT; opt-in, bflk_set_channel_split): the serial channel loop gets shorter by the cluster size for the price of the
+// exchange.  Constants fitted to cfg3 / cfg2 / cfg1 single-frame launches on B200 (profiles/r2c_latency_shapes.txt): cycles
+// per channel step with 1 / 2 / 3 / 4 / 5 warps per scheduler (a lone warp is bound by its own load -> FFMA2 -> branch
+// latencies, four by the issue port); clusters of 8 are not used (16 warps x 8 ranks: 82 us where 16 x 4 takes 76 -- they
+// do not all fit at once next to 200 KB of shared memory per CTA).
+// Returns warps = 0 (throughput shape) for larger calls; otherwise the shape with the smallest estimate -- the larger CTA
+// (fewer copies of the rows staged) on ties, no split unless it wins by 10 %.
+static void latency_shape(long long n_tiles, long long pair_ctas, int sms, int n_stage, bool may_split, int *warps, int *split) {
+    *warps = 0;
+    *split = 1;
+    if (((n_tiles + 15) / 16) * pair_ctas >= 2LL * sms) return;
+    static const double step[6] = {0, 455, 538, 658, 880, 1100};
+    const double fixed = 19650, exchange = 6000;
+    double best_t = 0;
+    for (int sp = 1; sp <= (may_split ? 4 : 1); sp *= 2) {
+        if (sp > 1 && n_stage / sp < 4) break;
+        for (int w = 16; w >= 2; w--) {
+            const long long ctas = ((n_tiles + w - 1) / w) * pair_ctas * sp;
+            const double chans = 8.0 * ((n_stage + sp - 1) / sp);
+            const double t = (double)((ctas + sms - 1) / sms) * (chans * step[(w + 3) / 4] + fixed + (sp > 1 ? exchange : 0));
+            if (!*warps || t < best_t * (sp > *split ? 0.9 : 1.0) - 1e-9) { *warps = w; *split = sp; best_t = t; }
+        }
+    }
+    if (*warps == 16 && *split == 1) *warps = 0;
+}
+
 int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
                         float *power_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
@@ -644,19 +683,23 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
         // a call with few block pairs cannot fill the SMs with 16-warp CTAs (one cfg3 frame: 16 CTAs, each walking 512
         // channels with four warps per scheduler): smaller CTAs trade per-SM efficiency for latency.  The shape is part of
         // the table layout, so a handle that alternates between single frames and large batches rebuilds its tables.
-        int want_warps = 0;
+        int want_warps = 0, want_split = 1;
         if (h->rows > 0 && h->cols > 0 && h->tuning.tile_warps == 0) {
             const int nblk = N <= 256 ? 1 : (N - 2 + 253) / 254;
             const long long pairs = ((long long)n_frames * nblk + 1) / 2;
+            const int ppc = h->tuning.tile_pairs > 0 ? h->tuning.tile_pairs : std::max(1, std::min(8, 512 / std::max(1, usable)));
             const int row0 = (h->dir_first / h->cols) & ~1, row1 = (h->dir_first + h->dir_count - 1) / h->cols;
             const long long n_tiles = (long long)((row1 - row0) / 2 + 1) * ((h->cols + 1) / 2);
-            if (((n_tiles + 11) / 12) * pairs * 20 < (long long)h->sm_count * 9) {      // even 12-warp CTAs fill < 45 % of the SMs
-                want_warps = ((n_tiles + 7) / 8) * pairs * 20 >= (long long)h->sm_count * 9 ? 8 : 4;
-            }
+            latency_shape(n_tiles, (pairs + ppc - 1) / ppc, h->sm_count, (usable + kTileCC - 1) / kTileCC,
+                          h->kernel_choice != 2 && h->allow_ksplit && !h->tuning.no_ksplit,
+                          &want_warps, &want_split);
         }
-        if (h->chunk_mode) want_warps = 0;   // the chunk loop built the throughput-shape tables before it queued anything
+        if (want_warps > 0 && h->tuning.lat_warps >= 2 && h->tuning.lat_warps <= 16) want_warps = h->tuning.lat_warps;   // experiments
+        if (want_warps > 0 && h->tuning.lat_split >= 1 && h->allow_ksplit) want_split = h->tuning.lat_split;
+        if (h->chunk_mode) { want_warps = 0; want_split = 1; }   // the chunk loop built the throughput-shape tables before it queued anything
         int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, want_warps);
         if (rc) return rc;
+        h->tile_geom.ksplit = das_tile_ksplit_ok(h->tile_geom, want_split) ? want_split : 1;
         tiled = h->tiles_usable && (wire || (!(row_stride & 1) && !((uintptr_t)stream_dev & 7)));  // packed rows: 8-byte loads
         if (h->kernel_choice != 0 && !tiled)
             return h->fail(BFLK_ERR_STATE, "bflk_power_map: the register-tiled kernel does not fit this grid (offset spread %d of at most %d, %d stage buffers fit shared memory)",

@@ -71,6 +71,9 @@ struct Tuning {
     int tile_stages = 0;     // BFLK_TILE_STAGES: 3 or 4 stage buffers
     int tile_pairs = 0;      // BFLK_TILE_PAIRS: block pairs per CTA
     int tile_mode = -1;      // BFLK_TILE_MODE: 0 one window per 2x2 tile, 1 / 2 one window per direction pair
+    int lat_warps = 0;       // BFLK_LAT_WARPS / BFLK_LAT_SPLIT: force the CTA shape / cluster size of small calls (measurements)
+    int lat_split = 0;
+    int no_ksplit = 0;       // BFLK_NO_KSPLIT=1: small calls never split the channels across a thread-block cluster
     int chunk_mib = 0;       // BFLK_CHUNK_MIB: host batches are uploaded in chunks of about this size
     int chunk_one_stream = 0;  // BFLK_CHUNK_ONE_STREAM=1: the chunks' kernels on one stream (round-2 behaviour, for comparison)
 };
@@ -88,6 +91,7 @@ struct TileGeometry {
     int row_bytes = 0;   // bytes per packed row: the even-aligned copy followed by the copy shifted by one sample pair
     int stages = 0;      // stage buffers that fit shared memory (4 or 3; 0 = the variant does not fit at all)
     int pairs_per_cta = 0;  // 0 = automatic
+    int ksplit = 1;      // 2 / 4 / 8: a thread-block cluster of that size splits the channels of a block pair (small calls, two-FMA form)
 };
 
 // ---- lane-broadcast kernel (das_bcast.cu) -----------------------------------------------------------------
@@ -157,6 +161,7 @@ struct bflk_handle {
     int64_t launches = 0;
     int kernel_choice = 0;  // 0 auto, 1 generic, 2 tiled
     int kernel_last = 0;    // what the last power-map call ran
+    bool allow_ksplit = false;  // bflk_set_channel_split: small two-FMA calls may split the channels across a thread-block cluster
 
     // geometry + mask (host copies are the source of truth; device copies feed the table kernels)
     bool have_geometry = false;
@@ -179,7 +184,7 @@ struct bflk_handle {
     bool tiles_valid = false;
     bool tiles_usable = false;   // false: grid shape / spreads do not fit the tiled kernel
     int tiles_fast = 0;          // the tables were built for the two-FMA variant
-    int tiles_want_warps = 0;    // ... and for this CTA shape (0: throughput shape; 4 / 8: latency shape of small calls)
+    int tiles_want_warps = 0;    // ... and for this CTA shape (0: throughput shape; 2..15: latency shape of small calls, latency_warps())
     int32_t n_tiles = 0;
     int32_t tile_smax = 0;       // compiled window slack the tables need
     bflk::DevBuf<char> d_tiles;             // tile_table_entries(n_tiles, usable) TileEntry / TileEntryFast, layout above
@@ -360,6 +365,8 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
 // shared memory the variant needs with `stages` stage buffers
 size_t das_tile_smem_bytes(const TileGeometry &g, int stages);
 size_t das_tile_packed_bytes(const TileArgs &a);
+// can this geometry split the channels of a block pair across a cluster of `split` CTAs (two-FMA 16-warp variants only)?
+bool das_tile_ksplit_ok(const TileGeometry &g, int split);
 size_t das_tile_entry_bytes(const TileGeometry &g);
 
 // ---- das_bcast.cu -----------------------------------------------------------------------------------

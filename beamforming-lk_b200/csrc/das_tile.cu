@@ -171,7 +171,11 @@ struct KernelArgs {
 // DUAL: two NCH-chunk windows per channel, one per direction pair (tile tables built with mode 1 / 2), NCH 6 or 7
 // FAST: two-FMA form acc += g s[i+1]; acc += f s[i] (TileEntryFast tables; power within 1e-4 of the reference instead of
 //       bit-identical delayed sums) -- 16 FFMA2 per (direction, channel) and no other FP instruction.
-template <int NCH, int kWarps, bool DUAL = false, bool FAST = false>
+// KSPLIT: the CTAs of a thread-block cluster (grid.z = cluster size 2 / 4 / 8) split the CHANNELS of a block pair between
+//       them and add their partial delayed sums through distributed shared memory, in rank order, before the epilogue.
+//       For calls too small to fill the SMs (a live worker's single frame: cfg3 is 16 CTAs): the serial channel loop gets
+//       shorter by the cluster size.  The channel sum is re-associated (rank sums added at the end), so FAST only.
+template <int NCH, int kWarps, bool DUAL = false, bool FAST = false, bool KSPLIT = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kEnt = FAST ? (DUAL ? (int)sizeof(TileEntryFastDual) : (int)sizeof(TileEntryFast)) : (int)sizeof(TileEntry);
@@ -188,6 +192,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_stage = (a.usable + kCC - 1) / kCC;
+    // pipeline stages st_first, st_first + st_step, ... of every block pair are this CTA's: all of them, unless a cluster splits
+    // the channels -- then round robin, so every rank sees the same mix of near and far microphones (the share of second
+    // windows, i.e. the cost of a stage, depends on where on the array its channels sit)
+    int st_first = 0, st_step = 1;
+    unsigned crank = 0, csize = 1;
+    if constexpr (KSPLIT) {
+        asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+        st_first = (int)crank;
+        st_step = (int)csize;
+    }
     const int tile0 = blockIdx.x * nwarps;
     const int my_tile = min(tile0 + warp, a.n_tiles - 1);
     const bool active = tile0 + warp < a.n_tiles;  // idle warps of the last tile group only keep the pipeline moving
@@ -219,10 +234,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
         bulk_g2s(dst + stage_rows, a.tiles + ((size_t)blockIdx.x * n_stage + st) * (nwarps * kCC) * kEnt, tile_bytes, full);
     };
     // (pair, chunk) of the stage kStages ahead of the one being consumed, advanced once per stage by every warp
-    int npair = pair_lo, nst = 0;
+    int npair = pair_lo, nst = st_first;
     for (int g = 0; g < kStages; g++) {
         if (threadIdx.x == 0 && npair < pair_hi) issue(npair, nst, g);
-        if (++nst == n_stage) { nst = 0; npair++; }
+        if ((nst += st_step) >= n_stage) { nst = st_first; npair++; }
     }
 
     const uint32_t lane_off = 80u * lane;  // 8 pairs = 4 chunks = 5 padded chunks per lane
@@ -271,14 +286,45 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_tile_kernel(KernelArgs a) 
                 // all of this warp's reads of the buffer have completed (their values were consumed above)
                 if (atomicInc(&done_cnt[buf], nwarps - 1) == (unsigned)(nwarps - 1) && npair < pair_hi) issue(npair, nst, buf);
             }
-            if (++nst == n_stage) { nst = 0; npair++; }
+            if ((nst += st_step) >= n_stage) { nst = st_first; npair++; }
             if (++buf == kStages) { buf = 0; ph ^= 1; }
     };
     if constexpr (DUAL && FAST) {
 #pragma unroll 1
-        for (int st = 0; st < n_stage; st++) stage(st);
+        for (int st = st_first; st < n_stage; st += st_step) stage(st);
     } else {
-        for (int st = 0; st < n_stage; st++) stage(st);
+        for (int st = st_first; st < n_stage; st += st_step) stage(st);
+    }
+
+    if constexpr (KSPLIT) {
+        // Tile t (= warp t of every rank) is finished by rank t % cluster size.  Every warp PUSHES its partial sums into the
+        // finishing rank's shared memory (st.shared::cluster: nobody waits for a remote load), slot [source rank][t / cluster
+        // size], 8 KB each, over the stage buffers -- which is why the first cluster barrier is there: every CTA must be done
+        // with its rows first (no bulk copy is in flight: one block pair per CTA in this mode).  After the second barrier the
+        // finishing warp adds the partials IN RANK ORDER from its own shared memory (its own included, read back the same
+        // way: the result does not depend on which rank finishes the tile) and runs the epilogue; the others are done.
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        const int nfw = (nwarps + (int)csize - 1) / (int)csize;
+        const unsigned dest = (unsigned)warp % csize;
+        const int wl = warp / (int)csize;
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem + (uint32_t)((((int)crank * nfw + wl) * 8192) + lane * 16)), "r"(dest));
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            asm volatile("st.shared::cluster.v2.b64 [%0], {%1, %2};" ::"r"(remote + (uint32_t)(j * 512)), "l"(acc[j >> 2][2 * (j & 3)]),
+                         "l"(acc[j >> 2][2 * (j & 3) + 1]) : "memory");
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (dest != crank) continue;
+        for (int q = 0; q < (int)csize; q++) {
+            const uint32_t src = smem + (uint32_t)(((q * nfw + wl) * 8192) + lane * 16);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                u64 v0, v1;
+                lds128(v0, v1, src + (uint32_t)(j * 512));
+                acc[j >> 2][2 * (j & 3)] = q == 0 ? v0 : add2(acc[j >> 2][2 * (j & 3)], v0);
+                acc[j >> 2][2 * (j & 3) + 1] = q == 0 ? v1 : add2(acc[j >> 2][2 * (j & 3) + 1], v1);
+            }
+        }
     }
 
     // ---- epilogue: MA = 0.5 out[j] - 0.25 (out[j+1] + out[j-1]); power = sum MA^2 (mimo.cpp:131-137) ----
@@ -395,16 +441,17 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
         if (score > best + 1e-9) { best = score; g.warps = cand[i]; g.stages = stages; }
     }
     g.tmpl_warps = g.warps;
-    if (want_warps > 0 && want_warps < 10 && g.stages >= 3) {
+    if (want_warps > 0 && want_warps <= 16 && g.stages >= 3) {
         // latency shape (single-frame calls): fewer warps per CTA than the throughput shape, run on the largest compiled
         // variant (its register budget is an upper bound); the stage ring of a smaller CTA always fits if the large one does
+        const int tmpl = can16 && !exact_dual7 ? 16 : 12;
         TileGeometry t = g;
-        t.warps = want_warps;
+        t.warps = std::min(want_warps, tmpl);
         int stages = tuning && tuning->tile_stages == 3 ? 3 : kMaxStages;
         if (das_tile_smem_bytes(t, stages) > 227 * 1024) stages = 3;
         if (das_tile_smem_bytes(t, stages) <= 227 * 1024) {
-            g.tmpl_warps = can16 && !exact_dual7 ? 16 : 12;
-            g.warps = want_warps;
+            g.tmpl_warps = tmpl;
+            g.warps = t.warps;
             g.stages = stages;
         }
     }
@@ -413,23 +460,45 @@ TileGeometry das_tile_geometry(int history, int max_delay, int max_span, int n_t
     return g;
 }
 
+bool das_tile_ksplit_ok(const TileGeometry &g, int split) {
+    // the exchange area (8 KB per (source rank, tile finished here)) reuses the stage buffers' rows
+    return (split == 2 || split == 4) && g.fast && g.tmpl_warps == 16 && g.stages >= 3 &&
+           (size_t)split * ((g.warps + split - 1) / split) * 8192 <= (size_t)g.stages * kCC * g.row_bytes;
+}
+
 size_t das_tile_entry_bytes(const TileGeometry &g) {
     return g.fast ? (g.mode ? sizeof(TileEntryFastDual) : sizeof(TileEntryFast)) : sizeof(TileEntry);
 }
 
-template <int NCH, int WARPS, bool DUAL = false, bool FAST = false>
+template <int NCH, int WARPS, bool DUAL = false, bool FAST = false, bool KSPLIT = false>
 static cudaError_t launch_main(const KernelArgs &k, dim3 grid, size_t smem, cudaStream_t st) {
     // the attribute is per device and only ever grows: set it when a larger request appears there, not per launch
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || smem > configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(das_tile_kernel<NCH, WARPS, DUAL, FAST, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
     const int warps = k.launch_warps > 0 && k.launch_warps <= WARPS ? k.launch_warps : WARPS;
-    das_tile_kernel<NCH, WARPS, DUAL, FAST><<<grid, warps * 32, smem, st>>>(k);
+    if constexpr (KSPLIT) {
+        // grid.z CTAs = one thread-block cluster per (tile group, block pair): they split the channels
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(warps * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 1;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = grid.z;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, das_tile_kernel<NCH, WARPS, DUAL, FAST, KSPLIT>, k);
+    }
+    das_tile_kernel<NCH, WARPS, DUAL, FAST, KSPLIT><<<grid, warps * 32, smem, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -505,9 +574,24 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
         ks.n_pairs = np;
         // a CTA lives ~0.6 us per channel: with few channels several block pairs per CTA hide its ramp-up and epilogue
         ks.pairs_per_cta = a.geom.pairs_per_cta > 0 ? a.geom.pairs_per_cta : std::max(1, std::min(8, 512 / std::max(1, a.usable)));
-        dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta);
+        // channel split across a cluster (latency shape of small calls): compiled for the 16-warp two-FMA variants
+        const int ksplit = a.geom.fast && tw == 16 && a.geom.ksplit > 1 ? a.geom.ksplit : 1;
+        if (ksplit > 1) ks.pairs_per_cta = 1;
+        dim3 grid((a.n_tiles + kWarps - 1) / kWarps, (np + ks.pairs_per_cta - 1) / ks.pairs_per_cta, ksplit);
         if (hook) hook(hook_ctx, 0, true, st);
-        if (a.geom.fast && a.geom.mode != 0) {
+        if (ksplit > 1 && a.geom.mode != 0) {
+            if (a.geom.nch == 6) e = launch_main<6, 16, true, true, true>(ks, grid, smem, st);
+            else e = launch_main<7, 16, true, true, true>(ks, grid, smem, st);
+        } else if (ksplit > 1) {
+            switch (a.geom.nch) {
+                case 5: e = launch_main<5, 16, false, true, true>(ks, grid, smem, st); break;
+                case 6: e = launch_main<6, 16, false, true, true>(ks, grid, smem, st); break;
+                case 7: e = launch_main<7, 16, false, true, true>(ks, grid, smem, st); break;
+                case 8: e = launch_main<8, 16, false, true, true>(ks, grid, smem, st); break;
+                case 9: e = launch_main<9, 16, false, true, true>(ks, grid, smem, st); break;
+                default: e = launch_main<10, 16, false, true, true>(ks, grid, smem, st); break;
+            }
+        } else if (a.geom.fast && a.geom.mode != 0) {
             if (a.geom.nch == 6) {
                 switch (tw) {
                     case 10: e = launch_main<6, 10, true, true>(ks, grid, smem, st); break;

@@ -397,19 +397,33 @@ def miso_bench(bflk, torch, dev, local, calls=300):
 
 
 def single_frame_latency(bflk, name, local, calls=200):
+    """One live frame through bflk_power_map (what a Worker adapter calls once per 5.24 ms): host window in, host map out.
+    The window is page-locked like the adapters' snapshot buffer (`auto_pageable`: an ordinary numpy array instead)."""
+    import ctypes as C
+    import torch
     from bflk import synth
     c = cases.CONFIGS[name]
     w = bflk.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"], device=local)
     win = synth.make_stream(synth.tile_geometry(cases.origins(c["nx"], c["ny"])), c["W"])
+    pin = torch.from_numpy(win).pin_memory()
+    res = torch.empty(c["rows"] * c["cols"], dtype=torch.float32).pin_memory()
     out = {}
-    for kernel, label in ((0, "auto"), (2, "bit_identical")):
+    # auto = two-FMA form; channel_split = the same with bflk_set_channel_split (a thread-block cluster splits the channels
+    # of the frame: deterministic, within the 1e-4 bar, but not the bits a large batch gives); bit_identical = kernel 2
+    for kernel, split, src, label in ((0, False, pin.data_ptr(), "auto"), (0, True, pin.data_ptr(), "channel_split"),
+                                      (2, False, pin.data_ptr(), "bit_identical"), (0, False, win.ctypes.data, "auto_pageable")):
         w.set_kernel(kernel)
+        w.set_channel_split(split)
+
+        def call():
+            rc = w._L.bflk_power_map(w._h, C.c_void_p(src), C.c_void_p(res.data_ptr()))
+            assert rc == 0
         for _ in range(20):
-            w.update(win)
+            call()
         t = []
         for _ in range(calls):
             t0 = time.perf_counter()
-            w.update(win)
+            call()
             t.append((time.perf_counter() - t0) * 1e6)
         out[label] = {"p50_us": float(np.percentile(t, 50)), "p95_us": float(np.percentile(t, 95))}
     w.close()

@@ -132,6 +132,13 @@ int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_
  * 4 = register-tiled kernel in two-FMA form (f*s[i] + (1-f)*s[i+1]: as accurate as the reference against exact
  * arithmetic, power maps within the 1e-4 bar, ~13 % faster than 2).  Automatic = 4 when the grid tiles, else 3, else 1. */
 int bflk_set_kernel(bflk_handle *h, int32_t which);
+/* Latency option for calls too small to fill the GPU (a live worker's single frame, MIMOWorker::update once per 5.24 ms,
+ * src/dsp/mimo.cpp:97-151): on != 0 lets the two-FMA form (kernel 0 / 4) split the CHANNELS of a frame across a thread-block
+ * cluster of 2 / 4 / 8 CTAs, whose partial delayed sums are added through distributed shared memory in a fixed order before
+ * the power epilogue (cfg3 single frame: 16 CTAs become 128).  The result is deterministic and within the same 1e-4 bar, but
+ * the channel sum is associated differently than in a large batch, so "a batch gives the same bits as its frames one by
+ * one" holds only with the option off (the default).  Kernel 2 never splits (its sums stay bit-identical to delay()). */
+int bflk_set_channel_split(bflk_handle *h, int32_t on);
 /* Which kernel the last power-map call used (1 generic, 2 tiled exact, 3 lane-broadcast, 4 tiled two-FMA; 0 = none yet), the
  * largest offset spread inside a direction tile (or tile pair) for the current grid, and the window chunks of the tiled
  * variant in use. */

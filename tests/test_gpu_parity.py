@@ -434,6 +434,42 @@ def test_batch_equals_single_frames(bf, oracle, kernel):
     assert rel_err(pb[3], po) <= POWER_RTOL
 
 
+@pytest.mark.parametrize("name", ["cfg3", "cfg2", "cfg1"])
+def test_channel_split_latency_mode(bf, oracle, name):
+    """bflk_set_channel_split: a single frame's channels split across a thread-block cluster (partial delayed sums added
+    through distributed shared memory in rank order).  Within the 1e-4 bar of the oracle with the same peak, deterministic,
+    a masked channel list and a direction range work, kernel 2 ignores the option (bit-identical sums), and the default
+    (option off) is untouched."""
+    c = cases.CONFIGS[name]
+    w = make(bf, c)
+    window = _synth_window(bf, c)
+    off, fr = w.tables()
+    po = oracle.ref_mimo_update(window, off, fr, n_threads=8) if oracle.ref() is not None else oracle.mimo_update(window, off, fr)
+    p_off = w.update(window)
+    w.set_channel_split(True)
+    p_on = w.update(window)
+    assert rel_err(p_on, po) <= POWER_RTOL and int(np.argmax(p_on)) == int(np.argmax(po))
+    assert rel_err(p_on, p_off) <= 2e-5
+    assert np.array_equal(w.update(window), p_on)                    # deterministic
+    w.set_kernel(2)
+    p2 = w.update(window)
+    w.set_channel_split(False)
+    assert np.array_equal(w.update(window), p2)                      # kernel 2 never splits
+    w.set_kernel(0)
+    assert np.array_equal(w.update(window), p_off)
+    # a masked, ragged channel list (stages of the ranks do not divide evenly) and a direction range
+    w.set_channel_split(True)
+    C = window.shape[0]
+    mask = np.setdiff1d(np.arange(C, dtype=np.int32), np.arange(5, C, 7, dtype=np.int32)).astype(np.int32)
+    w.set_channel_mask(mask)
+    n_dir = c["rows"] * c["cols"]
+    first, count = n_dir // 3, n_dir // 2 + 1
+    w.set_direction_range(first, count)
+    pm = w.update(window)
+    pom = oracle.mimo_update(window, off[first:first + count], fr[first:first + count], index=mask)
+    assert pm.shape == (count,) and rel_err(pm, pom) <= POWER_RTOL
+
+
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_ragged_direction_ranges_and_masks(bf, oracle, kernel):
     c = cases.CONFIGS["cfg2"]

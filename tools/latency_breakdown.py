@@ -16,9 +16,10 @@ import cases  # noqa: E402
 
 for name in ("cfg1", "cfg2", "cfg3"):
     c = cases.CONFIGS[name]
-    for kernel in (0, 2):
+    for kernel, split in ((0, True), (0, False), (2, False)):
         w = bflk.MIMOWorker(cases.origins(c["nx"], c["ny"]), c["rows"], c["cols"], c["fov"])
         w.set_kernel(kernel)
+        w.set_channel_split(split)
         win = synth.make_stream(synth.tile_geometry(cases.origins(c["nx"], c["ny"])), 1024)
         pin = torch.from_numpy(win).pin_memory()
         out = torch.empty(c["rows"] * c["cols"], dtype=torch.float32).pin_memory()
@@ -40,6 +41,6 @@ for name in ("cfg1", "cfg2", "cfg3"):
             w.enable_timing(False)
             res[label] = (np.percentile(t, 50), np.percentile(t, 95), das_ms / das_n * 1e3, pack_ms / max(1, pack_n) * 1e3)
         k = w.kernel_info()
-        print(f"{name} kernel {k[0]}: pageable p50 {res['pageable'][0]:.0f} us (p95 {res['pageable'][1]:.0f}); page-locked p50 {res['pinned'][0]:.0f} us "
+        print(f"{name} kernel {k[0]}{' + channel split' if split else ''}: pageable p50 {res['pageable'][0]:.0f} us (p95 {res['pageable'][1]:.0f}); page-locked p50 {res['pinned'][0]:.0f} us "
               f"(p95 {res['pinned'][1]:.0f}) of which delay-and-sum kernel {res['pinned'][2]:.0f} us, pack {res['pinned'][3]:.0f} us")
         w.close()
