@@ -30,7 +30,7 @@ SYMBOLS = [
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_grid_shape", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch", "bflk_power_map_batch_submit", "bflk_power_map_batch_wait", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
-    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_set_channel_split", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
+    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_set_channel_split", "bflk_launch_shape", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
@@ -101,6 +101,7 @@ def load_library():
     L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_set_kernel.argtypes = [vp, i32]
     L.bflk_set_channel_split.argtypes = [vp, i32]
+    L.bflk_launch_shape.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.bflk_launch_count.argtypes = [vp]
     L.bflk_launch_count.restype = i64
     L.bflk_get_kernel.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
@@ -164,6 +165,16 @@ def shard_plan(n_directions, n_frames, n_ranks, rank, dir_groups=0):
     if rc != 0:
         raise BflkError(rc, f"bflk_shard_plan({n_directions}, {n_frames}, {n_ranks}, {dir_groups}, {rank})")
     return a.value, b.value, c.value, d.value
+
+
+def launch_shape(rows, cols, n_channels, n_frames=1, frame_len=256, n_sms=148, channel_split=False):
+    """(warps per CTA, cluster size of the channel split) a power-map call gets (bflk_launch_shape; needs no device)."""
+    L = load_library()
+    w, s = C.c_int32(), C.c_int32()
+    rc = L.bflk_launch_shape(rows, cols, n_channels, frame_len, n_frames, n_sms, 1 if channel_split else 0, C.byref(w), C.byref(s))
+    if rc != 0:
+        raise BflkError(rc, f"bflk_launch_shape({rows}, {cols}, {n_channels}, {frame_len}, {n_frames}, {n_sms})")
+    return w.value, s.value
 
 
 def comm_unique_id():

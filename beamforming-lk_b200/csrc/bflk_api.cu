@@ -396,6 +396,20 @@ int bflk_set_channel_split(bflk_handle *h, int32_t on) {
     return BFLK_OK;
 }
 
+int bflk_launch_shape(int32_t rows, int32_t cols, int32_t n_channels, int32_t frame_len, int32_t n_frames, int32_t n_sms,
+                      int32_t channel_split, int32_t *warps, int32_t *split) {
+    if (rows <= 0 || cols <= 0 || n_channels <= 0 || frame_len < 256 || n_frames <= 0 || n_sms <= 0 || !warps || !split) return BFLK_ERR_INVALID;
+    const int nblk = frame_len <= 256 ? 1 : (frame_len - 2 + 253) / 254;
+    const long long pairs = ((long long)n_frames * nblk + 1) / 2;
+    const int ppc = std::max(1, std::min(8, 512 / n_channels));
+    int w = 0, sp = 1;
+    bflk::latency_shape((long long)((rows + 1) / 2) * ((cols + 1) / 2), (pairs + ppc - 1) / ppc, n_sms, (n_channels + kTileCC - 1) / kTileCC,
+                        channel_split != 0, &w, &sp);
+    *warps = w;
+    *split = sp;
+    return BFLK_OK;
+}
+
 int64_t bflk_launch_count(const bflk_handle *h) { return h ? h->launches : 0; }
 
 int bflk_get_kernel(const bflk_handle *h, int32_t *last_used, int32_t *tile_span, int32_t *window_chunks) {
@@ -624,7 +638,7 @@ static int ensure_bcast(bflk_handle *h) {
 // do not all fit at once next to 200 KB of shared memory per CTA).
 // Returns warps = 0 (throughput shape) for larger calls; otherwise the shape with the smallest estimate -- the larger CTA
 // (fewer copies of the rows staged) on ties, no split unless it wins by 10 %.
-static void latency_shape(long long n_tiles, long long pair_ctas, int sms, int n_stage, bool may_split, int *warps, int *split) {
+void bflk::latency_shape(long long n_tiles, long long pair_ctas, int sms, int n_stage, bool may_split, int *warps, int *split) {
     *warps = 0;
     *split = 1;
     if (((n_tiles + 15) / 16) * pair_ctas >= 2LL * sms) return;

@@ -407,6 +407,7 @@ cudaError_t launch_map_targets(const float *d_power, int rows, int cols, int max
 int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
                   float *power_dev, void *cuda_stream);
 int ensure_tiles(bflk_handle *h, int fast, int want_warps = 0);
+void latency_shape(long long n_tiles, long long pair_ctas, int sms, int n_stage, bool may_split, int *warps, int *split);
 int64_t min_stream_samples(const bflk_handle *h, int n_frames);
 // frames per chunk of a host batch of n_frames (whole CTA waves of the tiled kernel where it applies) and the samples a
 // frame needs beyond its own N

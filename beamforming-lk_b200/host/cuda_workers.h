@@ -20,7 +20,8 @@
 //
 // Numerics.  The adapters select the kernel whose delayed sums are bit-identical to delay() (bflk_set_kernel 2): a live
 // worker processes one frame per 5.24 ms and has no use for the 13 % the two-FMA form saves in batch throughput.
-// -DBFLK_WORKER_AUTOMATIC_KERNEL keeps the library's automatic choice.
+// -DBFLK_WORKER_AUTOMATIC_KERNEL keeps the library's automatic choice (two-FMA form, power within 1e-4) and lets a thread-block
+// cluster split the channels of the frame (bflk_set_channel_split): the lowest latency, not bit-identical sums.
 //
 // Build modes: by default the reference headers are included; with -DBFLK_STANDIN_HEADERS the minimal
 // stand-ins under tests/standin are used instead (Eigen / OpenCV are not installed in the build image).
@@ -68,6 +69,8 @@ inline bflk_handle *make_handle(const Antenna &antenna, int n_elements, const ch
     }
 #ifndef BFLK_WORKER_AUTOMATIC_KERNEL
     bflk_set_kernel(h, 2);  // delayed sums bit-identical to delay() (src/dsp/delay.cpp:16-26)
+#else
+    bflk_set_channel_split(h, 1);  // a live worker has one frame at a time: latency shape (cfg3 frame 223 -> 105 us)
 #endif
     return h;
 }

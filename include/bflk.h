@@ -139,6 +139,13 @@ int bflk_set_kernel(bflk_handle *h, int32_t which);
  * the channel sum is associated differently than in a large batch, so "a batch gives the same bits as its frames one by
  * one" holds only with the option off (the default).  Kernel 2 never splits (its sums stay bit-identical to delay()). */
 int bflk_set_channel_split(bflk_handle *h, int32_t on);
+/* The CTA shape a power-map call gets (pure arithmetic, no device needed): rows x cols directions (2x2 tiles), n_channels
+ * usable channels, n_frames frames of frame_len samples on a GPU with n_sms SMs.  warps = warps per CTA, 0 = the throughput
+ * shape (16-warp CTAs; every call that fills two waves of them); split = cluster size of the channel split (1 = none; 2 / 4
+ * only with channel_split != 0).  The model behind it (waves x (fixed cost + channels x cycles per channel step for the warps
+ * sharing a scheduler)) is fitted to B200 measurements: profiles/r2c_latency_shapes.txt. */
+int bflk_launch_shape(int32_t rows, int32_t cols, int32_t n_channels, int32_t frame_len, int32_t n_frames, int32_t n_sms,
+                      int32_t channel_split, int32_t *warps, int32_t *split);
 /* Which kernel the last power-map call used (1 generic, 2 tiled exact, 3 lane-broadcast, 4 tiled two-FMA; 0 = none yet), the
  * largest offset spread inside a direction tile (or tile pair) for the current grid, and the window chunks of the tiled
  * variant in use. */

@@ -64,3 +64,29 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(bflk.BflkError) as e:
         bflk.Beamformer()
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_launch_shape_of_small_calls():
+    """bflk_launch_shape (pure arithmetic): the CTA shape of calls too small to fill a B200, as measured in
+    profiles/r2c_latency_shapes.txt -- and the throughput shape (0) for everything that fills two waves of 16-warp CTAs."""
+    import bflk
+    # one live frame
+    assert bflk.launch_shape(32, 32, 512) == (4, 1)                          # cfg3: 64 four-warp CTAs, one warp per scheduler
+    assert bflk.launch_shape(32, 32, 512, channel_split=True) == (8, 4)      # 128 eight-warp CTAs in clusters of 4
+    assert bflk.launch_shape(64, 64, 256) == (8, 1)                          # cfg2: 128 CTAs
+    assert bflk.launch_shape(64, 64, 256, channel_split=True) == (16, 2)
+    assert bflk.launch_shape(100, 100, 64) == (12, 1)                        # cfg1: 209 CTAs in two waves beat 157 in two
+    assert bflk.launch_shape(100, 100, 64, channel_split=True) == (12, 1)    # 8 stages: nothing to split
+    # batches that fill the GPU keep the throughput shape, with or without the option
+    for split in (False, True):
+        assert bflk.launch_shape(32, 32, 512, n_frames=592, channel_split=split) == (0, 1)
+        assert bflk.launch_shape(256, 256, 512, n_frames=1, frame_len=4096, channel_split=split) == (0, 1)
+    # every answer is launchable: 2..16 warps, cluster of 1 / 2 / 4, at least 4 pipeline stages per rank
+    for rows, cols, ch, nf in [(2, 2, 64, 1), (8, 8, 64, 3), (9, 9, 512, 1), (24, 24, 256, 6), (32, 32, 512, 5), (16, 128, 448, 2)]:
+        for split in (False, True):
+            for sms in (148, 132, 8):
+                w, s = bflk.launch_shape(rows, cols, ch, n_frames=nf, n_sms=sms, channel_split=split)
+                assert (w == 0 or 2 <= w <= 16) and s in (1, 2, 4) and (split or s == 1)
+                assert s == 1 or ((ch + 7) // 8) // s >= 4
+    with pytest.raises(bflk.BflkError):
+        bflk.launch_shape(0, 32, 512)
