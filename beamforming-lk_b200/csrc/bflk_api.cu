@@ -934,16 +934,21 @@ static int host_batch_enqueue(bflk_handle *h, const float *stream, int64_t n_sam
     for (int k = 0; k < n_chunks; k++) {
         const int f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
         const int64_t need = k == n_chunks - 1 ? last_needed : std::min<int64_t>(last_needed, (int64_t)(f0 + nf) * N + tail);
+        cudaStream_t cs = two_streams ? h->chunk_stream[k & 1] : h->stream;
+        // a synchronous single-chunk call (one live frame) has nothing to overlap: its upload goes on the compute stream
+        // itself, no event hop between two streams on the latency path
+        cudaStream_t up = (n_chunks == 1 && !reuse_after) ? cs : h->copy_stream;
         if (need > copied) {
             BFLK_CUDA(h, cudaMemcpy2DAsync(d_in.p + copied, n_samples * sizeof(float), stream + copied,
                                            n_samples * sizeof(float), (need - copied) * sizeof(float), C,
-                                           cudaMemcpyHostToDevice, h->copy_stream));
+                                           cudaMemcpyHostToDevice, up));
             copied = need;
         }
-        cudaStream_t cs = two_streams ? h->chunk_stream[k & 1] : h->stream;
         h->scratch_slot = two_streams ? (k & 1) : 0;
-        BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
-        BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->chunk_events[k], 0));
+        if (up != cs) {
+            BFLK_CUDA(h, cudaEventRecord(h->chunk_events[k], h->copy_stream));
+            BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->chunk_events[k], 0));
+        }
         float *pk = d_out.p + (size_t)f0 * h->dir_count;
         rc = power_map_dev(h, d_in.p + (size_t)f0 * N, n_samples, copied - (int64_t)f0 * N, nf, pk, cs);
         if (rc) return rc;

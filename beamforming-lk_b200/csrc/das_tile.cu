@@ -387,6 +387,12 @@ __global__ void finalize_kernel(const float *__restrict__ partial, int n_frames,
 // ---- host side ---------------------------------------------------------------------------------------------------
 int das_tile_max_span() { return 11; }
 
+// experiment switch (read once): BFLK_NO_PACK_CARVEOUT=1 leaves the pack kernels' L1 / shared split to the driver
+static bool getenv_once_no_carveout() {
+    static const bool v = [] { const char *e = getenv("BFLK_NO_PACK_CARVEOUT"); return e && e[0] == '1'; }();
+    return v;
+}
+
 size_t das_tile_entry_bytes(const TileGeometry &g);
 
 size_t das_tile_smem_bytes(const TileGeometry &g, int stages) {
@@ -555,6 +561,19 @@ cudaError_t launch_das_tile(const TileArgs &a, int sm_count, cudaStream_t st, in
     k.stages = stages;
     k.launch_warps = kWarps;
 
+    // the main kernel needs (nearly) all of an SM's shared memory: ask for the same L1 / shared split for the pack pre-pass
+    // (it streams, an L1 hit rate does not matter to it), so the SMs do not have to be reconfigured between the two launches
+    // of every call
+    static bool carveout_set[64] = {false};
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !carveout_set[dev] && !getenv_once_no_carveout()) {
+            cudaFuncSetAttribute(pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(pack_wire_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set[dev] = true;
+        }
+    }
     // grid.y / grid.z are limited to 65535: process the pairs in slabs
     const int max_slab = 32768;
     for (int p0 = 0; p0 < n_pairs; p0 += max_slab) {

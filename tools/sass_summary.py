@@ -28,7 +28,7 @@ for line in out.splitlines():
             w = re.search(r"\.(64|128|256)", m.group(2))
             op += "." + (w.group(1) if w else "32")
         per[name][op] += 1
-KEY = ["FFMA2", "FADD2", "FFMA", "FADD", "LDS.128", "LDS.64", "LDS.32", "LDG.32", "UBLKCP", "SYNCS", "BRA", "LOP3", "IADD3", "ATOMS", "HMMA", "UTCMMA", "UTMALDG"]
+KEY = ["FFMA2", "FADD2", "FFMA", "FADD", "LDS.128", "LDS.64", "LDS.32", "LDG.32", "UBLKCP", "SYNCS", "BRA", "LOP3", "IADD3", "ATOMS", "UCGABAR_ARV", "MAPA", "HMMA", "UTCMMA", "UTMALDG"]
 tot = collections.Counter()
 print(f"SASS opcode summary of {os.path.relpath(LIB, ROOT)} (sm_100a); columns: total instructions, then selected mnemonics")
 print(f"{'kernel':78s} {'total':>7s} " + " ".join(f"{k:>7s}" for k in KEY))
