@@ -974,6 +974,146 @@ __device__ __forceinline__ void {name}<{nch}>(u64 (&acc)[4][{KW}], uint32_t ent,
 # shared memory 79 % busy and 0.45 of the FP32 peak on every configuration (profiles/README.md).
 
 
+
+def gen_k6(dual=True, KK=6):
+    """Experiment (tile_bench only): the two-FMA stage loop with KK = 6 sample pairs per lane (192-sample blocks).  The lane
+    stride is three 16-byte chunks -- odd, so LDS.128 is conflict free WITHOUT pad chunks: one address per window instead of
+    four class offsets, 48-byte entries (oa | ob | dl | - ; f[4] ; g[4]), a 5-chunk window (6 + 1 + span 3 pairs), 48
+    accumulator registers -> ~90 registers, 20 warps per CTA (five per scheduler).  Fewer FFMA2 per dispatch (12 instead
+    of 16) against fewer address / load instructions and a fifth warp to fill the issue slots."""
+    nch = (KK + 1 + 3 + 1) // 2
+    nw = 2 * nch
+    kmax = nw - (KK + 1)
+    nbits = max(1, kmax.bit_length())
+    n_acc = 4 * KK
+    ENT, ROWR, END = f"%{n_acc}", f"%{n_acc + 1}", f"%{n_acc + 2}"
+    esz = 48
+    AK = lambda r, k: f"%{r * KK + k}"
+    L = []
+    emit = L.append
+
+    def body(r, D):
+        for k in range(KK):
+            emit(f"    fma.rn.f32x2 {AK(r, k)}, gg{r}, w{D + k + 1}, {AK(r, k)};")
+        for k in range(KK):
+            emit(f"    fma.rn.f32x2 {AK(r, k)}, ff{r}, w{D + k}, {AK(r, k)};")
+
+    def preds(r):
+        for b in range(nbits):
+            emit(f"    and.b32 x, dl, {1 << (6 * r + b)};")
+            emit(f"    setp.ne.b32 p{b}, x, 0;")
+
+    def window(o):
+        for m in range(nch):
+            emit(f"    ld.shared.v2.b64 {{w{2 * m}, w{2 * m + 1}}}, [{o}+{16 * m}];")
+
+    def load_entry_head():
+        emit(f"    ld.shared.v4.u32 {{oa, ob, dl, x}}, [{ENT}];")
+
+    def load_entry_fracs():
+        emit(f"    ld.shared.v4.f32 {{f0, f1, f2, f3}}, [{ENT}+16];")
+        emit(f"    ld.shared.v4.f32 {{g0, g1, g2, g3}}, [{ENT}+32];")
+
+    def entry_tail():
+        emit(f"    add.u32 oa, oa, {ROWR};")
+        preds(0)
+
+    def subtree(r, lo, bit, tag):
+        if bit < 0:
+            emit(f"    bra.uni B{r}_{lo};")
+            return
+        hi = lo + (1 << bit)
+        if hi > kmax:
+            subtree(r, lo, bit - 1, tag)
+            return
+        lab = f"T{tag}_{hi}_{bit}"
+        emit(f"    @p{bit} bra.uni {lab};")
+        subtree(r, lo, bit - 1, tag)
+        emit(f"{lab}:")
+        subtree(r, hi, bit - 1, tag)
+
+    need = set()
+
+    def tree_from(r, dd):
+        for b in reversed(range(nbits)):
+            want = (dd >> b) & 1
+            base = ((dd >> (b + 1)) << (b + 1)) | ((1 - want) << b)
+            if base > kmax:
+                continue
+            need.add((r, base, b))
+            emit(f"    @{'!' if want else ''}p{b} bra.uni S{r}_{base}_{b};")
+
+    emit("{")
+    emit(f"    .reg .pred p<{nbits}>, ploop, q;")
+    emit("    .reg .b32 x, dl, oa, ob;")
+    emit("    .reg .f32 f<4>, g<4>;")
+    emit(f"    .reg .b64 ff<4>, gg<4>, w<{nw}>;")
+    load_entry_head()
+    load_entry_fracs()
+    entry_tail()
+    emit("TOP:")
+    window("oa")
+    for r in range(4):
+        emit(f"    mov.b64 ff{r}, {{f{r}, f{r}}};")
+        emit(f"    mov.b64 gg{r}, {{g{r}, g{r}}};")
+    tree_from(0, 0)
+    for dd in range(kmax + 1):
+        for r in range(4):
+            emit(f"B{r}_{dd}:")
+            if r == 0:
+                preds(1)
+                body(r, dd)
+                tree_from(1, dd)
+            elif r == 1:
+                preds(2)
+                if dual:
+                    emit(f"    and.b32 x, dl, {1 << 28};")
+                    emit("    setp.ne.b32 q, x, 0;")
+                body(r, dd)
+                if dual:
+                    # no join point: a block this short would be if-converted into five predicated loads that still issue
+                    # when the tile fits window A; the same-window path gets its own copy of the dispatch instead (SWS_dd)
+                    emit(f"    @q bra.uni SWS_{dd};")
+                    emit(f"    add.u32 ob, ob, {ROWR};")
+                    window("ob")
+                tree_from(2, dd)
+            elif r == 2:
+                preds(3)
+                body(r, dd)
+                tree_from(3, dd)
+            else:
+                emit(f"    add.u32 {ENT}, {ENT}, {esz};")
+                load_entry_head()
+                emit(f"    setp.ne.u32 ploop, {ENT}, {END};")
+                body(r, dd)
+                load_entry_fracs()
+                entry_tail()
+                emit("    @ploop bra.uni TOP;")
+                emit("    bra.uni DONE;")
+    if dual:
+        for dd in range(kmax + 1):
+            emit(f"SWS_{dd}:")
+            tree_from(2, dd)
+            emit(f"    bra.uni B2_{dd};")
+    for (r, base, b) in sorted(need):
+        emit(f"S{r}_{base}_{b}:")
+        subtree(r, base, b - 1, f"{r}_{base}_{b}")
+    emit("DONE:")
+    emit("}")
+    asm = "\n".join(f'        "{ln}\\n"' for ln in L)
+    outs = ", ".join([f'"+l"(acc[{r}][{k}])' for r in range(4) for k in range(KK)] + ['"+r"(ent)'])
+    name = "tile_stage_k6_dual" if dual else "tile_stage_k6"
+    return f"""// KK = {KK}: {'two windows' if dual else 'window'} of {nw} sample pairs, deltas 0..{kmax}, unpadded rows (lane stride {KK // 2} chunks)
+__device__ __forceinline__ void {name}(u64 (&acc)[4][{KK}], uint32_t ent, uint32_t row, uint32_t end) {{
+    asm volatile(
+{asm}
+        : {outs}
+        : "r"(row), "r"(end)
+        : "memory");
+}}
+"""
+
+
 import sys
 if "--fast" in sys.argv:
     print("// GENERATED by tools/gen_tile_asm.py --fast -- do not edit.  See that script for the why.")
@@ -987,6 +1127,11 @@ __device__ __forceinline__ void tile_stage_fast_dual(u64 (&acc)[4][8], uint32_t 
         print(gen_fast(nch))
     for nch in (6, 7):
         print(gen_fast(nch, dual=True))
+    sys.exit(0)
+if "--k6" in sys.argv:
+    print("// GENERATED by tools/gen_tile_asm.py --k6 -- do not edit.  Experiment for tools/ubench/tile_bench.cu.")
+    print(gen_k6(dual=True))
+    print(gen_k6(dual=False))
     sys.exit(0)
 if "--k16" in sys.argv:
     print("// GENERATED by tools/gen_tile_asm.py --k16 -- do not edit.  See that script for the why.")

@@ -29,8 +29,9 @@ typedef unsigned long long u64;
 #endif
 #include WIDE_INC
 #include "k16.inc"   // python ../gen_tile_asm.py --k16 > k16.inc
+#include "k6.inc"    // python ../gen_tile_asm.py --k6 > k6.inc
 
-enum Variant { FAST_SINGLE = 0, FAST_DUAL = 1, WIDE = 2, WIDE_EXACT = 3, EXACT_SINGLE = 4, EXACT_DUAL = 5, K16_SINGLE = 6, K16_DUAL = 7 };
+enum Variant { FAST_SINGLE = 0, FAST_DUAL = 1, WIDE = 2, WIDE_EXACT = 3, EXACT_SINGLE = 4, EXACT_DUAL = 5, K16_SINGLE = 6, K16_DUAL = 7, K6_DUAL = 8, K6_SINGLE = 9 };
 
 struct Args {
     const char *entries;   // [n_sets][warps][cc][ent]
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) bench_kernel(Args a) {
     for (int i = threadIdx.x; i < a.n_sets * set_bytes / 4; i += blockDim.x)
         reinterpret_cast<uint32_t *>(ents)[i] = reinterpret_cast<const uint32_t *>(a.entries)[i];
     __syncthreads();
-    constexpr int NACC = (V == K16_SINGLE || V == K16_DUAL) ? 64 : 32;
+    constexpr int NACC = (V == K16_SINGLE || V == K16_DUAL) ? 64 : (V == K6_DUAL || V == K6_SINGLE) ? 24 : 32;
     u64 acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i] = 0ull;
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) bench_kernel(Args a) {
         if constexpr (V == WIDE) tile_stage_wide<NCH>(*reinterpret_cast<u64(*)[2][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == K16_SINGLE) tile_stage_k16<NCH>(*reinterpret_cast<u64(*)[4][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == K16_DUAL) tile_stage_k16_dual<NCH>(*reinterpret_cast<u64(*)[4][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
+        if constexpr (V == K6_DUAL) tile_stage_k6_dual(*reinterpret_cast<u64(*)[4][6]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
+        if constexpr (V == K6_SINGLE) tile_stage_k6(*reinterpret_cast<u64(*)[4][6]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == WIDE_EXACT) tile_stage_wide_exact<NCH>(*reinterpret_cast<u64(*)[2][16]>(acc), tiles_s, row, tiles_s + a.cc * a.ent_bytes);
         if constexpr (V == EXACT_SINGLE || V == EXACT_DUAL) {
             uint32_t e0, e1;
@@ -108,12 +111,13 @@ static const double kTileSpanFine[2] = {0.65, 0.35};
 template <int V, int NCH, int WARPS>
 static void run(const char *name, int sms, int max_q, double same_window_share, const double *span_p, int n_span) {
     constexpr bool k16 = V == K16_SINGLE || V == K16_DUAL;
+    constexpr bool k6 = V == K6_DUAL || V == K6_SINGLE;
     const int cc = (V == WIDE || V == WIDE_EXACT || k16) ? 4 : 8;
-    const int lane_chunks = (V == WIDE || V == WIDE_EXACT || k16) ? 8 : 4;
+    const int lane_chunks = (V == WIDE || V == WIDE_EXACT || k16) ? 8 : (k6 ? 3 : 4);
     const int row_chunks = max_q + lane_chunks * 31 + NCH + 1;
-    const int copy_bytes = 16 * ((lane_chunks == 8 ? padded8(row_chunks - 1) : padded4(row_chunks - 1)) + 1);
+    const int copy_bytes = k6 ? 16 * row_chunks : 16 * ((lane_chunks == 8 ? padded8(row_chunks - 1) : padded4(row_chunks - 1)) + 1);
     const int row_bytes = 2 * copy_bytes;
-    const int ent_bytes = V == FAST_SINGLE ? 64 : V == FAST_DUAL ? 80 : (V == WIDE || V == WIDE_EXACT) ? 48 : V == K16_SINGLE ? 80 : V == K16_DUAL ? 112 : 32;
+    const int ent_bytes = k6 ? 48 : V == FAST_SINGLE ? 64 : V == FAST_DUAL ? 80 : (V == WIDE || V == WIDE_EXACT) ? 48 : V == K16_SINGLE ? 80 : V == K16_DUAL ? 112 : 32;
     const int n_sets = 8;
     std::mt19937 rng(12345);
     auto pick_span = [&]() {
@@ -129,7 +133,24 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
                 auto window = [&](int &odd, int &q) { odd = rng() & 1; q = rng() % (max_q + 1); };
                 float fr[4];
                 for (int k = 0; k < 4; k++) fr[k] = std::uniform_real_distribution<float>(0, 1)(rng);
-                if (k16) {
+                if (k6) {
+                    uint32_t o2[2] = {0, 0}, dl = 0;
+                    float g[4];
+                    for (int k = 0; k < 4; k++) g[k] = 1.0f - fr[k];
+                    for (int w2 = 0; w2 < (V == K6_DUAL ? 2 : 1); w2++) {
+                        int odd, q; window(odd, q);
+                        o2[w2] = c * row_bytes + odd * copy_bytes + 16 * q;
+                        const int sp = pick_span();
+                        if (V == K6_DUAL) dl |= ((rng() & 1) ? (uint32_t)sp : ((uint32_t)sp << 6)) << (12 * w2);
+                        else {
+                            const int zero_slot = rng() & 3;
+                            for (int k = 0; k < 4; k++) dl |= (uint32_t)(k == zero_slot ? 0 : (sp ? rng() % (sp + 1) : 0)) << (6 * k);
+                            if (sp) dl = (dl & ~(63u << (6 * ((zero_slot + 1) & 3)))) | ((uint32_t)sp << (6 * ((zero_slot + 1) & 3)));
+                        }
+                    }
+                    if (V == K6_DUAL && std::uniform_real_distribution<double>(0, 1)(rng) < same_window_share) dl |= 1u << 28;
+                    memcpy(e, o2, 8); memcpy(e + 8, &dl, 4); memcpy(e + 16, fr, 16); memcpy(e + 32, g, 16);
+                } else if (k16) {
                     uint32_t oa[8], ob[8], dl = 0;
                     float g[4];
                     for (int k = 0; k < 4; k++) g[k] = 1.0f - fr[k];
@@ -206,7 +227,7 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
     CK(cudaMalloc(&d_out, (size_t)sms * WARPS * 32 * 4)); CK(cudaMalloc(&d_cyc, sms * 8));
     Args a{};
     a.entries = d_ents; a.n_sets = n_sets; a.cc = cc; a.ent_bytes = ent_bytes; a.row_bytes = row_bytes;
-    a.rows_bytes = cc * row_bytes; a.iters = 4096 / cc; a.lane_stride = lane_chunks == 8 ? 144 : 80; a.out = d_out; a.cyc = d_cyc;
+    a.rows_bytes = cc * row_bytes; a.iters = 4096 / cc; a.lane_stride = lane_chunks == 8 ? 144 : (k6 ? 48 : 80); a.out = d_out; a.cyc = d_cyc;
     const size_t smem = (size_t)a.rows_bytes + ents.size() + 256;
     if (smem > 227 * 1024) { printf("%-28s does not fit shared memory (%zu B)\n", name, smem); return; }
     CK(cudaFuncSetAttribute(bench_kernel<V, NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -215,7 +236,7 @@ static void run(const char *name, int sms, int max_q, double same_window_share, 
     CK(cudaMemcpy(cyc.data(), d_cyc, sms * 8, cudaMemcpyDeviceToHost));
     std::sort(cyc.begin(), cyc.end());
     const double c = (double)cyc[sms / 2], steps = (double)a.iters * cc;
-    const double frac = steps * (k16 ? 128 : 64) * 2 * (WARPS / 4.0) / c;
+    const double frac = steps * (k16 ? 128 : (k6 ? 48 : 64)) * 2 * (WARPS / 4.0) / c;
     printf("%-28s nch %2d warps %2d row %5d B  cycles/channel-step/warp %.1f  fraction of FFMA2 issue peak %.3f\n", name, NCH, WARPS,
            row_bytes, c / steps, frac);
     cudaFree(d_ents); cudaFree(d_out); cudaFree(d_cyc);
@@ -235,6 +256,10 @@ int main() {
     run<EXACT_SINGLE, 6, 16>("exact single (cfg5-like)", sms, 49, 0, span3, 4);
     // coarse grid (cfg3): two windows per 2x2 tile today vs one direction pair x 16 sample pairs per lane
     run<FAST_DUAL, 6, 16>("fast dual (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
+    run<K6_DUAL, 5, 20>("k6 dual 20 warps (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
+    run<K6_DUAL, 5, 16>("k6 dual 16 warps (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
+    run<K6_DUAL, 5, 20>("k6 dual 20 warps, 1 window", sms, 49, 1.0, kPairSpan, 4);
+    run<K6_SINGLE, 5, 20>("k6 single 20 warps (span 0..1)", sms, 49, 0, span1, 2);
     run<FAST_DUAL, 6, 16>("fast dual, always 1 window", sms, 49, 1.0, kPairSpan, 4);
     run<FAST_DUAL, 6, 16>("fast dual, always 2 windows", sms, 49, 0.0, kPairSpan, 4);
     run<EXACT_DUAL, 6, 16>("exact dual (cfg3-like)", sms, 49, 0.5, kPairSpan, 4);
