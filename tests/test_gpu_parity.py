@@ -529,6 +529,34 @@ def test_odd_shapes_vs_oracle(bf, oracle, tiles, rows, cols, fov, N, W, B, kerne
         assert int(np.argmax(p[b])) == int(np.argmax(po))
 
 
+@pytest.mark.parametrize("tiles,rows,cols,fov,N,W,B", [
+    ((2, 1), 31, 33, 120.0, 256, 1024, 3),         # 14 ragged stages over a cluster of 2, odd grid, half-empty last block pair
+    ((2, 2), 40, 40, 180.0, 256, 1024, 7),         # twelve-warp CTAs in clusters of 2
+    ((4, 2), 24, 24, 180.0, 256, 1024, 2),         # 10-chunk single window, clusters of 4
+    ((2, 2), 36, 30, 150.0, 512, 1536, 3),         # frames of 512 samples: overlapping blocks, partial sums + finalize
+    ((4, 2), 30, 36, 100.0, 1000, 2048, 1),
+    ((2, 2), 19, 19, 120.0, 256, 1024, 1),         # odd grid; four-warp CTAs in clusters of 4: every warp finishes a tile on another rank
+])
+def test_odd_shapes_with_channel_split(bf, oracle, tiles, rows, cols, fov, N, W, B):
+    """The cluster path of bflk_set_channel_split on ragged channel lists, odd grids, long frames and small batches."""
+    from bflk import synth
+    org = cases.origins(*tiles)
+    w = bf.MIMOWorker(org, rows, cols, fov, frame_len=N, history=256, window_len=W)
+    w.set_channel_split(True)
+    mask = np.array([i for i in range(64 * len(org)) if i % 7 != 3], np.int32)
+    w.set_channel_mask(mask)
+    assert bf.launch_shape(rows, cols, len(mask), n_frames=B, frame_len=N, channel_split=True)[1] > 1   # the case does split
+    stream = synth.make_stream(synth.tile_geometry(org), (B - 1) * N + W)
+    p = w.power_map_batch(stream, B)
+    assert w.kernel_info()[0] == 4
+    off, fr = w.tables()
+    for b in range(B):
+        po = oracle.mimo_update(np.ascontiguousarray(stream[:, b * N:b * N + W]), off, fr, index=mask, n=N)
+        assert rel_err(p[b], po) <= POWER_RTOL, (b, rel_err(p[b], po))
+        assert int(np.argmax(p[b])) == int(np.argmax(po))
+    assert np.array_equal(w.power_map_batch(stream, B), p)
+
+
 def test_power_map_from_wire_samples(bf, oracle):
     """int32 wire frames -> un-flip, / 2^23 -> power map, all on the device, against oracle ingest + MIMO update."""
     from bflk import synth
