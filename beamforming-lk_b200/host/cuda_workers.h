@@ -70,7 +70,7 @@ inline bflk_handle *make_handle(const Antenna &antenna, int n_elements, const ch
 #ifndef BFLK_WORKER_AUTOMATIC_KERNEL
     bflk_set_kernel(h, 2);  // delayed sums bit-identical to delay() (src/dsp/delay.cpp:16-26)
 #else
-    bflk_set_channel_split(h, 1);  // a live worker has one frame at a time: latency shape (cfg3 frame 223 -> 105 us)
+    bflk_set_channel_split(h, 1);  // a live worker has one frame at a time: latency shape (cfg3 frame 207 -> 89 us)
 #endif
     return h;
 }
