@@ -34,7 +34,7 @@ SYMBOLS = [
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
-    "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded", "bflk_power_map_batch_sharded_submit", "bflk_power_map_batch_sharded_wait",
+    "bflk_power_map_batch_sharded_dev", "bflk_power_map_batch_sharded_dev_submit", "bflk_power_map_batch_sharded_dev_join", "bflk_power_map_batch_sharded", "bflk_power_map_batch_sharded_submit", "bflk_power_map_batch_sharded_wait",
     "bflk_group_create", "bflk_group_destroy", "bflk_group_size", "bflk_group_handle", "bflk_group_last_error",
     "bflk_group_set_geometry", "bflk_group_set_tiled_geometry", "bflk_group_set_channel_mask", "bflk_group_set_grid_fov",
     "bflk_group_set_kernel", "bflk_group_power_map_batch", "bflk_group_power_map_batch_dev", "bflk_group_synchronize",
@@ -126,6 +126,8 @@ def load_library():
     L.bflk_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.bflk_shard_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.bflk_power_map_batch_sharded_dev.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_power_map_batch_sharded_dev_submit.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_power_map_batch_sharded_dev_join.argtypes = [vp, vp]
     L.bflk_power_map_batch_sharded.argtypes = [vp, vp, i64, i32, vp]
     L.bflk_power_map_batch_sharded_submit.argtypes = [vp, vp, i64, i32, vp]
     L.bflk_power_map_batch_sharded_wait.argtypes = [vp]
@@ -250,6 +252,14 @@ class Beamformer:
     def power_map_batch_sharded_dev(self, stream_dev_ptr, n_samples, n_frames, power_all_dev_ptr, cuda_stream=0):
         self._check(self._L.bflk_power_map_batch_sharded_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
                                                              C.c_void_p(power_all_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_sharded_dev_submit(self, stream_dev_ptr, n_samples, n_frames, power_all_dev_ptr, cuda_stream=0):
+        """kernels on cuda_stream, all-gather + assembly on the communicator's stream (bflk.h); complete after _dev_join"""
+        self._check(self._L.bflk_power_map_batch_sharded_dev_submit(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
+                                                                    C.c_void_p(power_all_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_sharded_dev_join(self, cuda_stream=0):
+        self._check(self._L.bflk_power_map_batch_sharded_dev_join(self._h, C.c_void_p(cuda_stream)))
 
     def power_map_batch_sharded_submit_ptr(self, stream_ptr, n_samples, n_frames, power_ptr):
         self._check(self._L.bflk_power_map_batch_sharded_submit(self._h, C.c_void_p(stream_ptr), n_samples, n_frames,

@@ -88,9 +88,20 @@ struct bflk_comm {
     nccl_comm_t sub = nullptr;   // the G_d ranks that share this rank's frame slice (== all when G_f == 1; null when G_d == 1)
     int n_ranks = 1, rank = 0, gd = 1, gf = 1, dgrp = 0, fgrp = 0;
     int planned_dirs = -1;       // grid size the direction range was set for
-    DevBuf<float> d_local;       // [nf][count] tight output of this rank's kernel when the shard is ragged
-    DevBuf<float> d_send;        // [nf_max][per] what the all-gather sends
-    DevBuf<float> d_gather;      // [G][nf_max][per]
+    // two sets: the synchronous calls use set 0; bflk_power_map_batch_sharded_dev_submit alternates, so the kernels of
+    // batch i + 1 fill one set while the all-gather of batch i still reads the other
+    DevBuf<float> d_local_[2];   // [nf][count] tight output of this rank's kernel when the shard is ragged
+    DevBuf<float> d_send_[2];    // [nf_max][per] what the all-gather sends
+    DevBuf<float> d_gather_[2];  // [G][nf_max][per]
+    int slot = 0;                // set in use by the call being enqueued
+    DevBuf<float> &d_local() { return d_local_[slot]; }
+    DevBuf<float> &d_send() { return d_send_[slot]; }
+    DevBuf<float> &d_gather() { return d_gather_[slot]; }
+    cudaStream_t gather_stream = nullptr;                    // collectives of submitted device batches
+    cudaEvent_t ev_computed[2] = {nullptr, nullptr};         // a set's kernels are done (gather may start)
+    cudaEvent_t ev_gathered[2] = {nullptr, nullptr};         // a set's all-gather + assembly are done (set reusable, maps complete)
+    bool gathered_recorded[2] = {false, false};
+    uint64_t dev_seq = 0;
     DevBuf<float> d_all;         // [B][D] assembled maps (host variant)
     DevBuf<float> d_slice[kRing];   // [C / G_d][Tj] rows this rank uploads
     DevBuf<float> d_chunk[kRing];   // [C][Tj] replicated chunk
@@ -193,11 +204,11 @@ int compute_shard(bflk_handle *h, const Plan &p, const float *stream_dev, int64_
     if (nf <= 0 || p.dir_count <= 0) return BFLK_OK;
     const int N = h->cfg.frame_len;
     const bool tight = p.dir_count == p.dir_per;
-    float *out = tight ? c->d_send.p + (size_t)out_row0 * p.dir_per : c->d_local.p + (size_t)out_row0 * p.dir_count;
+    float *out = tight ? c->d_send().p + (size_t)out_row0 * p.dir_per : c->d_local().p + (size_t)out_row0 * p.dir_count;
     int rc = power_map_dev(h, stream_dev + (size_t)f_rel0 * N, row_stride, n_samples - (int64_t)f_rel0 * N, nf, out, st);
     if (rc) return rc;
     if (!tight)
-        BFLK_CUDA(h, cudaMemcpy2DAsync(c->d_send.p + (size_t)out_row0 * p.dir_per, (size_t)p.dir_per * sizeof(float), out,
+        BFLK_CUDA(h, cudaMemcpy2DAsync(c->d_send().p + (size_t)out_row0 * p.dir_per, (size_t)p.dir_per * sizeof(float), out,
                                        (size_t)p.dir_count * sizeof(float), (size_t)p.dir_count * sizeof(float), nf,
                                        cudaMemcpyDeviceToDevice, st));
     return BFLK_OK;
@@ -206,9 +217,15 @@ int compute_shard(bflk_handle *h, const Plan &p, const float *stream_dev, int64_
 int reserve_maps(bflk_handle *h, const Plan &p, int B, bool need_all) {
     bflk_comm *c = h->comm;
     const size_t slice = (size_t)p.frame_per * p.dir_per;
-    BFLK_CUDA(h, c->d_send.reserve(slice));
-    BFLK_CUDA(h, c->d_gather.reserve(slice * c->n_ranks));
-    if (p.dir_count != p.dir_per) BFLK_CUDA(h, c->d_local.reserve((size_t)p.frame_per * p.dir_count));
+    const bool grows = slice > c->d_send().n || slice * c->n_ranks > c->d_gather().n ||
+                       (p.dir_count != p.dir_per && (size_t)p.frame_per * p.dir_count > c->d_local().n);
+    if (grows && c->gathered_recorded[c->slot]) {   // a submitted batch may still use the set that is about to be reallocated
+        BFLK_CUDA(h, cudaEventSynchronize(c->ev_gathered[c->slot]));
+        c->gathered_recorded[c->slot] = false;
+    }
+    BFLK_CUDA(h, c->d_send().reserve(slice));
+    BFLK_CUDA(h, c->d_gather().reserve(slice * c->n_ranks));
+    if (p.dir_count != p.dir_per) BFLK_CUDA(h, c->d_local().reserve((size_t)p.frame_per * p.dir_count));
     if (need_all) BFLK_CUDA(h, c->d_all.reserve((size_t)B * h->n_dir));
     return BFLK_OK;
 }
@@ -224,7 +241,7 @@ int gather_and_assemble(const std::vector<bflk_handle *> &hs, const std::vector<
         bflk_comm *c = h->comm;
         cudaSetDevice(h->cfg.device);
         const size_t slice = (size_t)plans[i].frame_per * plans[i].dir_per;
-        int r = n.AllGather(c->d_send.p, c->d_gather.p, slice, kNcclFloat, c->all, st[i]);
+        int r = n.AllGather(c->d_send().p, c->d_gather().p, slice, kNcclFloat, c->all, st[i]);
         if (r != 0) {
             n.GroupEnd();
             return h->fail(BFLK_ERR_CUDA, "ncclAllGather failed: %s", n.GetErrorString(r));
@@ -239,16 +256,20 @@ int gather_and_assemble(const std::vector<bflk_handle *> &hs, const std::vector<
         BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
         const Plan &p = plans[i];
         dim3 grid((h->n_dir + 255) / 256, B);
-        assemble_kernel<<<grid, 256, 0, st[i]>>>(h->comm->d_gather.p, B, h->n_dir, p.gd, p.frame_per, p.dir_per, out_dev[i]);
+        assemble_kernel<<<grid, 256, 0, st[i]>>>(h->comm->d_gather().p, B, h->n_dir, p.gd, p.frame_per, p.dir_per, out_dev[i]);
         BFLK_CUDA(h, cudaGetLastError());
         h->launches++;
     }
     return BFLK_OK;
 }
 
+// pipelined = false: everything on st (the maps are complete in stream order).  pipelined = true (one handle per process):
+// the kernels go on st, the all-gather + assembly on the communicator's own stream, in alternating buffer sets, so the
+// kernels of the next submitted batch run under this batch's collective; sharded_dev_join makes a stream wait for them.
 int sharded_dev(const std::vector<bflk_handle *> &hs, const std::vector<const float *> &stream_dev, int64_t n_samples,
-                int32_t n_frames, const std::vector<float *> &power_all_dev, const std::vector<cudaStream_t> &st) {
+                int32_t n_frames, const std::vector<float *> &power_all_dev, const std::vector<cudaStream_t> &st, bool pipelined = false) {
     std::vector<Plan> plans(hs.size());
+    std::vector<cudaStream_t> gst = st;
     for (size_t i = 0; i < hs.size(); i++) {
         bflk_handle *h = hs[i];
         int rc = check_sharded(h, "bflk_power_map_batch_sharded_dev");
@@ -258,12 +279,49 @@ int sharded_dev(const std::vector<bflk_handle *> &hs, const std::vector<const fl
             return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_sharded_dev: %lld samples per channel cannot hold %d frames", (long long)n_samples, n_frames);
         BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
         bflk_comm *c = h->comm;
+        c->slot = 0;
+        if (pipelined) {
+            if (!c->gather_stream) BFLK_CUDA(h, cudaStreamCreateWithFlags(&c->gather_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) {
+                if (!c->ev_computed[k]) BFLK_CUDA(h, cudaEventCreateWithFlags(&c->ev_computed[k], cudaEventDisableTiming));
+                if (!c->ev_gathered[k]) BFLK_CUDA(h, cudaEventCreateWithFlags(&c->ev_gathered[k], cudaEventDisableTiming));
+            }
+            c->slot = (int)(c->dev_seq++ & 1);
+            gst[i] = c->gather_stream;
+            // the batch that used this set two submits ago: its collective must be done before the kernels overwrite the set
+            if (c->gathered_recorded[c->slot]) BFLK_CUDA(h, cudaStreamWaitEvent(st[i], c->ev_gathered[c->slot], 0));
+        } else {
+            // a synchronous call after submitted batches: set 0 may still be in flight on the communicator's stream
+            for (int k = 0; k < 2; k++)
+                if (c->gathered_recorded[k]) BFLK_CUDA(h, cudaStreamWaitEvent(st[i], c->ev_gathered[k], 0));
+        }
         plans[i] = make_plan(h->n_dir, n_frames, c->n_ranks, c->gd, c->gf, c->rank);
         if ((rc = apply_direction_range(h, plans[i]))) return rc;
         if ((rc = reserve_maps(h, plans[i], n_frames, false))) return rc;
         if ((rc = compute_shard(h, plans[i], stream_dev[i], n_samples, n_samples, plans[i].frame_first, plans[i].frame_count, 0, st[i]))) return rc;
+        if (pipelined) {
+            BFLK_CUDA(h, cudaEventRecord(c->ev_computed[c->slot], st[i]));
+            BFLK_CUDA(h, cudaStreamWaitEvent(c->gather_stream, c->ev_computed[c->slot], 0));
+        }
     }
-    return gather_and_assemble(hs, plans, n_frames, power_all_dev, st);
+    int rc = gather_and_assemble(hs, plans, n_frames, power_all_dev, gst);
+    for (size_t i = 0; i < hs.size(); i++) {
+        bflk_comm *c = hs[i]->comm;
+        if (pipelined && rc == BFLK_OK) {
+            cudaSetDevice(hs[i]->cfg.device);
+            if (cudaEventRecord(c->ev_gathered[c->slot], c->gather_stream) == cudaSuccess) c->gathered_recorded[c->slot] = true;
+        }
+        c->slot = 0;
+    }
+    return rc;
+}
+
+int sharded_dev_join(bflk_handle *h, cudaStream_t st) {
+    bflk_comm *c = h->comm;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    for (int k = 0; k < 2; k++)
+        if (c->gathered_recorded[k]) BFLK_CUDA(h, cudaStreamWaitEvent(st, c->ev_gathered[k], 0));
+    return BFLK_OK;
 }
 
 // the ranks of a frame group must cut their slice into the same chunks (the input all-gather is a collective): each
@@ -320,6 +378,9 @@ int sharded_host(const std::vector<bflk_handle *> &hs, const float *stream, int6
             return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_sharded: %lld samples per channel cannot hold %d frames", (long long)n_samples, n_frames);
         BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
         bflk_comm *c = h->comm;
+        c->slot = 0;
+        for (int k = 0; k < 2; k++)   // device batches submitted earlier may still use buffer set 0 on the communicator's stream
+            if (c->gathered_recorded[k]) BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, c->ev_gathered[k], 0));
         plans[i] = make_plan(h->n_dir, n_frames, c->n_ranks, c->gd, c->gf, c->rank);
         if ((rc = apply_direction_range(h, plans[i]))) return rc;
         if ((rc = reserve_maps(h, plans[i], n_frames, true))) return rc;
@@ -557,7 +618,13 @@ void bflk::comm_release(bflk_handle *h) {
         c->d_slice[k].release();
         c->d_chunk[k].release();
     }
-    c->d_local.release(); c->d_send.release(); c->d_gather.release(); c->d_all.release(); c->d_agree.release();
+    for (int k = 0; k < 2; k++) {
+        c->d_local_[k].release(); c->d_send_[k].release(); c->d_gather_[k].release();
+        if (c->ev_computed[k]) cudaEventDestroy(c->ev_computed[k]);
+        if (c->ev_gathered[k]) cudaEventDestroy(c->ev_gathered[k]);
+    }
+    if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
+    c->d_all.release(); c->d_agree.release();
     if (nccl().ok()) {
         if (c->sub && c->sub != c->all) nccl().CommDestroy(c->sub);
         if (c->all) nccl().CommDestroy(c->all);
@@ -613,6 +680,22 @@ int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, in
                                      float *power_all_dev, void *cuda_stream) {
     if (!h) return BFLK_ERR_INVALID;
     return sharded_dev({h}, {stream_dev}, n_samples, n_frames, {power_all_dev}, {cuda_stream ? (cudaStream_t)cuda_stream : h->stream});
+}
+
+// Continuous operation on device-resident streams: the kernels of batch i + 1 (on cuda_stream) run under the all-gather and
+// assembly of batch i (on the communicator's own stream, alternating buffer sets); power_all_dev of every submitted batch is
+// complete for work enqueued on cuda_stream after _join.  Collective: every rank submits and joins alike.
+int bflk_power_map_batch_sharded_dev_submit(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                                            float *power_all_dev, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    return sharded_dev({h}, {stream_dev}, n_samples, n_frames, {power_all_dev}, {cuda_stream ? (cudaStream_t)cuda_stream : h->stream}, true);
+}
+
+int bflk_power_map_batch_sharded_dev_join(bflk_handle *h, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    int rc = check_sharded(h, "bflk_power_map_batch_sharded_dev_join");
+    if (rc) return rc;
+    return sharded_dev_join(h, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
 }
 
 int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out) {

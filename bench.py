@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 register-tiled (bit-identical sums), 3 lane-broadcast, 4 register-tiled two-FMA form")
     ap.add_argument("--dir-groups", type=int, default=0,
                     help="N > 1: direction groups G_d (ranks = G_d x frame groups); 0 = 2 when N is even; N = pure grid sharding")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: synchronous bflk_power_map_batch_sharded_dev per step instead of _dev_submit / _join")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip bit_identical / sustained / other_configs / latency / grid_shard")
@@ -253,15 +254,21 @@ class Timer:
         self.torch.cuda.synchronize()
 
     def timed(self, fn, steps, warmup):
-        """ms for `steps` calls of fn, CUDA events on the current stream, max over ranks."""
+        """ms for `steps` calls of fn, CUDA events on the current stream, max over ranks.  fn.finish (if any) runs after
+        the last call, inside the timed region: a step that leaves work on another stream joins it there."""
         torch = self.torch
+        finish = getattr(fn, "finish", None)
         for _ in range(warmup):
             fn()
+        if finish:
+            finish()
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish:
+            finish()
         e1.record()
         self.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
@@ -508,6 +515,13 @@ def run_ours(args, c, name):
     assert cs != 0
 
     def step_with(worker):
+        if world > 1 and not args.no_overlap:
+            # continuous operation: the all-gather + assembly of step i run on the communicator's stream under the kernels of
+            # step i + 1 (bflk_power_map_batch_sharded_dev_submit); the join after the last step is inside the timed region
+            def fn():
+                worker.power_map_batch_sharded_dev_submit(stream_dev.data_ptr(), T, B, out_all.data_ptr(), cs)
+            fn.finish = lambda: worker.power_map_batch_sharded_dev_join(cs)
+            return fn
         if world > 1:
             return lambda: worker.power_map_batch_sharded_dev(stream_dev.data_ptr(), T, B, out_all.data_ptr(), cs)
         return lambda: worker.power_map_batch_dev(stream_dev.data_ptr(), T, B, out_all.data_ptr(), cs)
@@ -715,7 +729,9 @@ def run_ours(args, c, name):
         roof_hbm = {"bound": "hbm", "achieved": alg_bytes / das_avg_s / 1e9 if das_n else None, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
                     "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
-        cfg.update(parallelism=f"{gd} direction groups x {gf} frame groups, sharded and gathered inside libbflk (NCCL)" if world > 1 else "single GPU",
+        cfg.update(parallelism=(f"{gd} direction groups x {gf} frame groups, sharded and gathered inside libbflk (NCCL)" +
+                                ("" if args.no_overlap else "; continuous operation: the all-gather of step i runs under the kernels of step i + 1 (bflk_power_map_batch_sharded_dev_submit / _join)"))
+                   if world > 1 else "single GPU",
                    directions_per_gpu=d_count, frames_per_gpu=f_count, kernel=roof["kernel"], tile_span=kinfo[1], window_chunks=kinfo[2])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

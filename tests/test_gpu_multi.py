@@ -66,3 +66,17 @@ def test_group_device_resident_all_ranks_get_full_maps():
         for o in outs:
             assert np.array_equal(o.cpu().numpy(), ref)
         g.close()
+
+
+@needs2
+def test_pipelined_device_batches_one_process_per_gpu():
+    """bflk_comm_init_rank (one process per GPU, as torchrun forms them) + bflk_power_map_batch_sharded_dev_submit / _join:
+    the check itself is tests/multi_dev_pipeline_check.py, run here under torch.distributed.run on two GPUs."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tests", "multi_dev_pipeline_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PIPELINE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
