@@ -30,7 +30,7 @@ SYMBOLS = [
     "bflk_set_grid_fov", "bflk_set_grid_tables", "bflk_set_grid_shape", "bflk_set_direction_range", "bflk_get_n_directions",
     "bflk_get_grid", "bflk_get_tables", "bflk_steer_tables", "bflk_power_map", "bflk_power_map_i32",
     "bflk_power_map_batch", "bflk_power_map_batch_submit", "bflk_power_map_batch_wait", "bflk_power_map_batch_i32", "bflk_power_map_batch_i32_dev",
-    "bflk_power_map_batch_dev", "bflk_set_kernel", "bflk_set_channel_split", "bflk_launch_shape", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
+    "bflk_power_map_batch_dev", "bflk_power_map_batch_dev_submit", "bflk_power_map_batch_dev_join", "bflk_set_kernel", "bflk_set_channel_split", "bflk_launch_shape", "bflk_get_kernel", "bflk_launch_count", "bflk_enable_timing",
     "bflk_kernel_time_ms", "bflk_fp32_peak_tflops", "bflk_set_window", "bflk_set_window_dev", "bflk_miso", "bflk_miso_dev", "bflk_monopulse", "bflk_set_fir",
     "bflk_pin_host", "bflk_unpin_host", "bflk_heatmap", "bflk_resize_u8", "bflk_targets", "bflk_calibrate", "bflk_ingest_i32",
     "bflk_comm_unique_id", "bflk_comm_init_rank", "bflk_comm_info", "bflk_shard_plan",
@@ -99,6 +99,8 @@ def load_library():
     L.bflk_power_map_batch_i32.argtypes = [vp, vp, i64, i32, vp]
     L.bflk_power_map_batch_i32_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.bflk_power_map_batch_dev.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_power_map_batch_dev_submit.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.bflk_power_map_batch_dev_join.argtypes = [vp, vp]
     L.bflk_set_kernel.argtypes = [vp, i32]
     L.bflk_set_channel_split.argtypes = [vp, i32]
     L.bflk_launch_shape.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -411,6 +413,14 @@ class Beamformer:
         """Device pointers (e.g. torch tensors' data_ptr()), asynchronous on cuda_stream."""
         self._check(self._L.bflk_power_map_batch_dev(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
                                                      C.c_void_p(power_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_dev_submit(self, stream_dev_ptr, n_samples, n_frames, power_dev_ptr, cuda_stream=0):
+        """Continuous operation (bflk.h): consecutive batches overlap on the handle's two compute streams; complete after _dev_join."""
+        self._check(self._L.bflk_power_map_batch_dev_submit(self._h, C.c_void_p(stream_dev_ptr), n_samples, n_frames,
+                                                            C.c_void_p(power_dev_ptr), C.c_void_p(cuda_stream)))
+
+    def power_map_batch_dev_join(self, cuda_stream=0):
+        self._check(self._L.bflk_power_map_batch_dev_join(self._h, C.c_void_p(cuda_stream)))
 
     def set_window(self, window):
         """Keep window [C][W] on the device: miso() / monopulse() with window=None then work on it (None forgets it)."""

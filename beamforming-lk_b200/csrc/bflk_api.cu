@@ -95,6 +95,7 @@ int bflk_destroy(bflk_handle *h) {
     for (int k = 0; k < 2; k++) {
         if (h->chunk_stream[k]) { cudaStreamSynchronize(h->chunk_stream[k]); cudaStreamDestroy(h->chunk_stream[k]); }
         if (h->chunk_join[k]) cudaEventDestroy(h->chunk_join[k]);
+        if (h->dev_in[k]) cudaEventDestroy(h->dev_in[k]);
     }
     h->d_packed_alt.release(); h->d_partial_alt.release();
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
@@ -679,6 +680,7 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
             if (!h->caller_event && cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming) != cudaSuccess) return;
             cudaEventRecord(h->caller_event, st);
             h->last_stream = st;
+            h->caller_event_is_overlapped = false;
         }
     } mark{h, st};
     DevBuf<char> &d_packed = h->scratch_slot ? h->d_packed_alt : h->d_packed;
@@ -819,11 +821,70 @@ int bflk::power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_str
     return BFLK_OK;
 }
 
+int bflk::power_map_dev_overlapped(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
+                                   float *power_dev, cudaStream_t caller, cudaStream_t *used) {
+    *used = caller;
+    if (!h->have_grid) return h->fail(BFLK_ERR_STATE, "bflk_power_map: set geometry and grid first");
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    const bool tiled_choice = !h->fir_phases && !h->wire_src && (h->kernel_choice == 0 || h->kernel_choice == 2 || h->kernel_choice == 4);
+    if (tiled_choice) {
+        // tables first (ensure_tiles synchronises the handle's stream when it has to build them), before anything is queued
+        int rc = ensure_tiles(h, h->kernel_choice != 2 ? 1 : 0, 0);
+        if (rc) return rc;
+    }
+    if (!tiled_choice || !h->tiles_usable || (row_stride & 1) || ((uintptr_t)stream_dev & 7))
+        return power_map_dev(h, stream_dev, row_stride, n_samples, n_frames, power_dev, caller);
+    const int slot = (int)(h->dev_seq++ & 1);
+    for (int i = 0; i < 2; i++) {
+        if (!h->chunk_stream[i]) BFLK_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking));
+        if (!h->chunk_join[i]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->chunk_join[i], cudaEventDisableTiming));
+        if (!h->dev_in[i]) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->dev_in[i], cudaEventDisableTiming));
+    }
+    if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
+    cudaStream_t cs = h->chunk_stream[slot];
+    // this batch's kernels wait for (a) the caller's stream having reached this call (its inputs), (b) whatever used the handle's
+    // scratch on another stream before the overlapped batches began.  Earlier overlapped batches need no wait: the same
+    // set's previous batch ran on this very stream, the other set's batch shares nothing with this one.
+    BFLK_CUDA(h, cudaEventRecord(h->dev_in[slot], caller));
+    BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->dev_in[slot], 0));
+    if (!h->caller_event_is_overlapped && h->last_stream) BFLK_CUDA(h, cudaStreamWaitEvent(cs, h->caller_event, 0));
+    h->chunk_mode = true;
+    h->scratch_slot = slot;
+    const int rc = power_map_dev(h, stream_dev, row_stride, n_samples, n_frames, power_dev, cs);
+    h->chunk_mode = false;
+    h->scratch_slot = 0;
+    if (rc) return rc;
+    // the handle's own stream collects the ends of all overlapped batches: caller_event then covers everything enqueued so far
+    BFLK_CUDA(h, cudaEventRecord(h->chunk_join[slot], cs));
+    BFLK_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_join[slot], 0));
+    BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
+    h->last_stream = h->stream;
+    h->caller_event_is_overlapped = true;
+    *used = cs;
+    return BFLK_OK;
+}
+
 extern "C" {
 
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream) {
     return power_map_dev(h, stream_dev, n_samples, n_samples, n_frames, power_dev, cuda_stream);
+}
+
+int bflk_power_map_batch_dev_submit(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                                    float *power_dev, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    if (!stream_dev || !power_dev || n_frames <= 0) return h->fail(BFLK_ERR_INVALID, "bflk_power_map_batch_dev_submit: null buffer or no frames");
+    cudaStream_t used;
+    return power_map_dev_overlapped(h, stream_dev, n_samples, n_samples, n_frames, power_dev, cuda_stream ? (cudaStream_t)cuda_stream : h->stream, &used);
+}
+
+int bflk_power_map_batch_dev_join(bflk_handle *h, void *cuda_stream) {
+    if (!h) return BFLK_ERR_INVALID;
+    BFLK_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->caller_event && h->last_stream && h->last_stream != st) BFLK_CUDA(h, cudaStreamWaitEvent(st, h->caller_event, 0));
+    return BFLK_OK;
 }
 
 }  // extern "C"
@@ -963,6 +1024,7 @@ static int host_batch_enqueue(bflk_handle *h, const float *stream, int64_t n_sam
         if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
         BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
         h->last_stream = h->stream;
+        h->caller_event_is_overlapped = false;
     }
     return BFLK_OK;
 }
@@ -1106,6 +1168,7 @@ int bflk_power_map_batch_i32(bflk_handle *h, const int32_t *frames, int64_t n_sa
         if (!h->caller_event) BFLK_CUDA(h, cudaEventCreateWithFlags(&h->caller_event, cudaEventDisableTiming));
         BFLK_CUDA(h, cudaEventRecord(h->caller_event, h->stream));
         h->last_stream = h->stream;
+        h->caller_event_is_overlapped = false;
     }
     BFLK_CUDA(h, cudaStreamSynchronize(h->stream));
     return BFLK_OK;

@@ -243,8 +243,12 @@ struct bflk_handle {
     cudaEvent_t chunk_join[2] = {nullptr, nullptr};
     bflk::DevBuf<char> d_packed_alt;
     bflk::DevBuf<float> d_partial_alt;
-    int scratch_slot = 0;         // which scratch set power_map_dev uses (1 only inside a chunked host batch)
+    int scratch_slot = 0;         // which scratch set power_map_dev uses (1 only inside a chunked host batch / overlapped device batches)
     bool chunk_mode = false;      // power_map_dev is being called by the chunk loop, which orders the streams itself
+    // device batches in continuous operation (power_map_dev_overlapped): they alternate between the two compute streams too
+    cudaEvent_t dev_in[2] = {nullptr, nullptr};   // "the caller's stream has reached the submit" (inputs ready)
+    uint64_t dev_seq = 0;
+    bool caller_event_is_overlapped = false;      // the latest caller_event covers overlapped batches only (see power_map_dev_overlapped)
 
     // optional kernel timing (bflk_enable_timing): event pairs recorded on the launching stream
     bool timing = false;
@@ -404,6 +408,13 @@ cudaError_t launch_map_targets(const float *d_power, int rows, int cols, int max
 
 // ---- bflk_api.cu internals used by multi.cu ---------------------------------------------------------------
 // stream_dev: first sample of frame 0; rows are row_stride floats apart and hold n_samples valid samples
+// Continuous operation: the same as power_map_dev, but enqueued on one of the handle's two compute streams (alternating, each
+// with its own scratch) after `caller` has reached this point; *used = the stream the kernels are on.  Consecutive calls
+// overlap: the pack pre-pass of batch i + 1 runs under the kernel of batch i and its CTAs fill the SMs the last CTAs of
+// batch i leave idle.  caller_event afterwards covers everything enqueued so far.  Falls back to power_map_dev on `caller`
+// (*used = caller) when the register-tiled kernels do not serve the grid.
+int power_map_dev_overlapped(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
+                             float *power_dev, cudaStream_t caller, cudaStream_t *used);
 int power_map_dev(bflk_handle *h, const float *stream_dev, int64_t row_stride, int64_t n_samples, int32_t n_frames,
                   float *power_dev, void *cuda_stream);
 int ensure_tiles(bflk_handle *h, int fast, int want_warps = 0);

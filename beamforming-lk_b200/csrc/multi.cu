@@ -198,19 +198,23 @@ int check_sharded(bflk_handle *h, const char *who) {
 }
 
 // local compute of one rank: its direction slice of frames [f0, f0 + nf) of a device-resident stream into c->d_send
+// used (optional): continuous operation -- the kernels go on one of the handle's two compute streams (power_map_dev_overlapped)
+// once st has reached this call; *used = that stream
 int compute_shard(bflk_handle *h, const Plan &p, const float *stream_dev, int64_t row_stride, int64_t n_samples, int f_rel0,
-                  int nf, int out_row0, cudaStream_t st) {
+                  int nf, int out_row0, cudaStream_t st, cudaStream_t *used = nullptr) {
     bflk_comm *c = h->comm;
+    if (used) *used = st;
     if (nf <= 0 || p.dir_count <= 0) return BFLK_OK;
     const int N = h->cfg.frame_len;
     const bool tight = p.dir_count == p.dir_per;
     float *out = tight ? c->d_send().p + (size_t)out_row0 * p.dir_per : c->d_local().p + (size_t)out_row0 * p.dir_count;
-    int rc = power_map_dev(h, stream_dev + (size_t)f_rel0 * N, row_stride, n_samples - (int64_t)f_rel0 * N, nf, out, st);
+    int rc = used ? power_map_dev_overlapped(h, stream_dev + (size_t)f_rel0 * N, row_stride, n_samples - (int64_t)f_rel0 * N, nf, out, st, used)
+                  : power_map_dev(h, stream_dev + (size_t)f_rel0 * N, row_stride, n_samples - (int64_t)f_rel0 * N, nf, out, st);
     if (rc) return rc;
     if (!tight)
         BFLK_CUDA(h, cudaMemcpy2DAsync(c->d_send().p + (size_t)out_row0 * p.dir_per, (size_t)p.dir_per * sizeof(float), out,
                                        (size_t)p.dir_count * sizeof(float), (size_t)p.dir_count * sizeof(float), nf,
-                                       cudaMemcpyDeviceToDevice, st));
+                                       cudaMemcpyDeviceToDevice, used ? *used : st));
     return BFLK_OK;
 }
 
@@ -298,9 +302,11 @@ int sharded_dev(const std::vector<bflk_handle *> &hs, const std::vector<const fl
         plans[i] = make_plan(h->n_dir, n_frames, c->n_ranks, c->gd, c->gf, c->rank);
         if ((rc = apply_direction_range(h, plans[i]))) return rc;
         if ((rc = reserve_maps(h, plans[i], n_frames, false))) return rc;
-        if ((rc = compute_shard(h, plans[i], stream_dev[i], n_samples, n_samples, plans[i].frame_first, plans[i].frame_count, 0, st[i]))) return rc;
+        cudaStream_t used = st[i];
+        if ((rc = compute_shard(h, plans[i], stream_dev[i], n_samples, n_samples, plans[i].frame_first, plans[i].frame_count, 0, st[i],
+                                pipelined ? &used : nullptr))) return rc;
         if (pipelined) {
-            BFLK_CUDA(h, cudaEventRecord(c->ev_computed[c->slot], st[i]));
+            BFLK_CUDA(h, cudaEventRecord(c->ev_computed[c->slot], used));
             BFLK_CUDA(h, cudaStreamWaitEvent(c->gather_stream, c->ev_computed[c->slot], 0));
         }
     }

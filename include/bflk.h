@@ -127,6 +127,15 @@ int bflk_power_map_batch_i32_dev(bflk_handle *h, const int32_t *frames_dev, int6
 /* Same with DEVICE pointers, asynchronous on cuda_stream (a cudaStream_t, NULL = the handle's stream). */
 int bflk_power_map_batch_dev(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
                              float *power_dev, void *cuda_stream);
+/* Continuous operation on DEVICE-resident streams: _dev_submit enqueues the batch on one of the handle's two compute streams
+ * (alternating, each with its own scratch) once cuda_stream has reached the call, and returns; consecutive batches overlap --
+ * the pack pre-pass of batch i + 1 runs under the kernel of batch i and its CTAs fill the SMs the last CTAs of batch i leave
+ * idle.  power_dev of every batch submitted so far is complete for work enqueued on cuda_stream after
+ * bflk_power_map_batch_dev_join(h, cuda_stream) (asynchronous: it enqueues a wait).  Batches in flight need their own
+ * power_dev.  Same bits as bflk_power_map_batch_dev.  Grids the register-tiled kernels do not serve run in stream order. */
+int bflk_power_map_batch_dev_submit(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
+                                    float *power_dev, void *cuda_stream);
+int bflk_power_map_batch_dev_join(bflk_handle *h, void *cuda_stream);
 /* Selects the kernel: 0 = automatic, 1 = generic per-direction kernel, 2 = register-tiled kernel with the reference's
  * exact operation triple (delayed sums bit-identical to delay(), src/dsp/delay.cpp:16-26), 3 = lane-broadcast kernel,
  * 4 = register-tiled kernel in two-FMA form (f*s[i] + (1-f)*s[i+1]: as accurate as the reference against exact
@@ -190,7 +199,8 @@ int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, in
 int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
 /* Continuous operation on DEVICE-resident streams (every rank alike): _dev_submit enqueues the rank's kernels on cuda_stream
  * and the all-gather + assembly on the communicator's own stream, in alternating buffer sets, so the kernels of batch i + 1
- * run under the collective of batch i (src/dsp/mimo.cpp:121-151: a rank's directions do not depend on the gather).
+ * run under the collective of batch i (src/dsp/mimo.cpp:121-151: a rank's directions do not depend on the gather), and the
+ * kernels themselves alternate between the handle's two compute streams like bflk_power_map_batch_dev_submit's.
  * power_all_dev of every batch submitted so far is complete for work enqueued on cuda_stream after
  * bflk_power_map_batch_sharded_dev_join(h, cuda_stream) (asynchronous: it enqueues a wait, the host does not block). */
 int bflk_power_map_batch_sharded_dev_submit(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,

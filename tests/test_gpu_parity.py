@@ -655,6 +655,73 @@ def test_submit_wait_pipeline_equals_synchronous_calls(bf):
     assert np.array_equal(again, want[3]) and np.array_equal(outs[0].numpy(), want[1])
 
 
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_overlapped_device_batches_equal_synchronous_calls(bf, kernel):
+    """bflk_power_map_batch_dev_submit / _join: device batches that overlap on the handle's two compute streams deliver the
+    bits of bflk_power_map_batch_dev -- alternating inputs, many batches in flight, a synchronous call and a host batch in
+    between, a mask change (tables rebuilt) while nothing is pending, and a grid the tiled kernels do not serve."""
+    import torch
+    c = cases.CONFIGS["cfg2"]
+    w = bf.MIMOWorker(cases.origins(c["nx"], c["ny"]), 24, 20, c["fov"])
+    w.set_kernel(kernel)
+    B = 9
+    T = (B - 1) * 256 + 1024
+    base = _synth_window(bf, c, n_samples=T)
+    ins = [torch.from_numpy(base * np.float32(1.0 + 0.5 * k)).cuda() for k in range(3)]
+    st = torch.cuda.Stream()
+    cs = st.cuda_stream
+
+    def sync_call(x):
+        o = torch.zeros((B, 480), dtype=torch.float32, device="cuda")
+        w.power_map_batch_dev(x.data_ptr(), T, B, o.data_ptr(), cs)
+        st.synchronize()
+        return o.cpu().numpy()
+    want = [sync_call(x) for x in ins]
+    outs = [torch.zeros((B, 480), dtype=torch.float32, device="cuda") for _ in range(8)]
+    order = [0, 1, 2, 2, 1, 0, 1, 2]
+    for k, i in enumerate(order):
+        w.power_map_batch_dev_submit(ins[i].data_ptr(), T, B, outs[k].data_ptr(), cs)
+    w.power_map_batch_dev_join(cs)
+    st.synchronize()
+    for k, i in enumerate(order):
+        assert np.array_equal(outs[k].cpu().numpy(), want[i]), k
+    # mixed with a synchronous device call and a host batch (both must order themselves against the batches in flight)
+    w.power_map_batch_dev_submit(ins[0].data_ptr(), T, B, outs[0].data_ptr(), cs)
+    w.power_map_batch_dev_submit(ins[1].data_ptr(), T, B, outs[1].data_ptr(), cs)
+    w.power_map_batch_dev(ins[2].data_ptr(), T, B, outs[2].data_ptr(), cs)
+    host = w.power_map_batch(base, B)
+    w.power_map_batch_dev_submit(ins[1].data_ptr(), T, B, outs[3].data_ptr(), cs)
+    w.power_map_batch_dev_join(cs)
+    st.synchronize()
+    assert np.array_equal(host, want[0])
+    for k, i in ((0, 0), (1, 1), (2, 2), (3, 1)):
+        assert np.array_equal(outs[k].cpu().numpy(), want[i]), k
+    # a mask change rebuilds the tables; the next submits use them
+    mask = np.arange(0, 256, 2, dtype=np.int32)
+    w.set_channel_mask(mask)
+    masked = sync_call(ins[0])
+    assert not np.array_equal(masked, want[0])
+    for k in range(3):
+        w.power_map_batch_dev_submit(ins[0].data_ptr(), T, B, outs[k].data_ptr(), cs)
+    w.power_map_batch_dev_join(cs)
+    st.synchronize()
+    for k in range(3):
+        assert np.array_equal(outs[k].cpu().numpy(), masked)
+    w.close()
+    # a grid too coarse for the tiled kernels: the submits run in stream order through the other kernels, same results
+    c3 = cases.CONFIGS["cfg3"]
+    w = bf.MIMOWorker(cases.origins(c3["nx"], c3["ny"]), 8, 8, c3["fov"])
+    x = torch.from_numpy(_synth_window(bf, c3, n_samples=T)).cuda()
+    o0 = torch.zeros((B, 64), dtype=torch.float32, device="cuda")
+    o1 = torch.zeros((B, 64), dtype=torch.float32, device="cuda")
+    w.power_map_batch_dev(x.data_ptr(), T, B, o0.data_ptr(), cs)
+    w.power_map_batch_dev_submit(x.data_ptr(), T, B, o1.data_ptr(), cs)
+    w.power_map_batch_dev_join(cs)
+    st.synchronize()
+    assert w.kernel_info()[0] != 4 and np.array_equal(o0.cpu().numpy(), o1.cpu().numpy())
+    w.close()
+
+
 def test_caller_supplied_tables_and_errors(bf, oracle):
     import bflk
     xyz = oracle.create_antenna()
