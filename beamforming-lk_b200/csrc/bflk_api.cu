@@ -71,6 +71,7 @@ int bflk_create(const bflk_config *cfg, bflk_handle **out) {
     h->tuning.tile_pairs = env_int("BFLK_TILE_PAIRS", 0);
     h->tuning.tile_mode = env_int("BFLK_TILE_MODE", -1);
     h->tuning.no_ksplit = env_int("BFLK_NO_KSPLIT", 0);
+    h->tuning.sharded_overlap_compute = env_int("BFLK_SHARDED_OVERLAP_COMPUTE", 0);
     h->tuning.lat_warps = env_int("BFLK_LAT_WARPS", 0);
     h->tuning.lat_split = env_int("BFLK_LAT_SPLIT", 0);
     h->tuning.chunk_mib = env_int("BFLK_CHUNK_MIB", 0);

@@ -73,6 +73,7 @@ struct Tuning {
     int tile_mode = -1;      // BFLK_TILE_MODE: 0 one window per 2x2 tile, 1 / 2 one window per direction pair
     int lat_warps = 0;       // BFLK_LAT_WARPS / BFLK_LAT_SPLIT: force the CTA shape / cluster size of small calls (measurements)
     int lat_split = 0;
+    int sharded_overlap_compute = 0;   // BFLK_SHARDED_OVERLAP_COMPUTE=1: sharded device batches alternate their kernels between two streams too
     int no_ksplit = 0;       // BFLK_NO_KSPLIT=1: small calls never split the channels across a thread-block cluster
     int chunk_mib = 0;       // BFLK_CHUNK_MIB: host batches are uploaded in chunks of about this size
     int chunk_one_stream = 0;  // BFLK_CHUNK_ONE_STREAM=1: the chunks' kernels on one stream (round-2 behaviour, for comparison)

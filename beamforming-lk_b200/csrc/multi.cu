@@ -302,9 +302,13 @@ int sharded_dev(const std::vector<bflk_handle *> &hs, const std::vector<const fl
         plans[i] = make_plan(h->n_dir, n_frames, c->n_ranks, c->gd, c->gf, c->rank);
         if ((rc = apply_direction_range(h, plans[i]))) return rc;
         if ((rc = reserve_maps(h, plans[i], n_frames, false))) return rc;
+        // The kernels stay on the caller's stream.  Alternating them between the handle's two compute streams as well
+        // (power_map_dev_overlapped, BFLK_SHARDED_OVERLAP_COMPUTE=1) gains 1.6 % on two GPUs (149.4 k vs 147.0 k maps/s) but
+        // loses on eight (529.6 k vs 573.7 k): with two buffer sets, batch i + 2 waits for the all-gather of batch i, which
+        // waits for kernels that now share the SMs with batch i + 1 -- a bubble per batch once a launch is only four waves.
         cudaStream_t used = st[i];
         if ((rc = compute_shard(h, plans[i], stream_dev[i], n_samples, n_samples, plans[i].frame_first, plans[i].frame_count, 0, st[i],
-                                pipelined ? &used : nullptr))) return rc;
+                                pipelined && h->tuning.sharded_overlap_compute ? &used : nullptr))) return rc;
         if (pipelined) {
             BFLK_CUDA(h, cudaEventRecord(c->ev_computed[c->slot], used));
             BFLK_CUDA(h, cudaStreamWaitEvent(c->gather_stream, c->ev_computed[c->slot], 0));

@@ -763,7 +763,7 @@ def run_ours(args, c, name):
                     "unit": "GB/s", "frac": alg_bytes / das_avg_s / 1e9 / pk["hbm_gbs"] if das_n else None,
                     "bytes_per_launch": alg_bytes, "peak_source": pk_kind}
         cfg.update(parallelism=(f"{gd} direction groups x {gf} frame groups, sharded and gathered inside libbflk (NCCL)" +
-                                ("" if args.no_overlap else "; continuous operation: consecutive steps alternate between two compute streams and the all-gather of step i runs under the kernels of step i + 1 (bflk_power_map_batch_sharded_dev_submit / _join)"))
+                                ("" if args.no_overlap else "; continuous operation: the all-gather of step i runs under the kernels of step i + 1 (bflk_power_map_batch_sharded_dev_submit / _join)"))
                    if world > 1 else ("single GPU" if args.no_overlap else "single GPU; continuous operation: consecutive steps alternate between the handle's two compute streams (bflk_power_map_batch_dev_submit / _join)"),
                    directions_per_gpu=d_count, frames_per_gpu=f_count, kernel=roof["kernel"], tile_span=kinfo[1], window_chunks=kinfo[2])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

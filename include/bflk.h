@@ -199,8 +199,7 @@ int bflk_power_map_batch_sharded_dev(bflk_handle *h, const float *stream_dev, in
 int bflk_power_map_batch_sharded(bflk_handle *h, const float *stream, int64_t n_samples, int32_t n_frames, float *power_out);
 /* Continuous operation on DEVICE-resident streams (every rank alike): _dev_submit enqueues the rank's kernels on cuda_stream
  * and the all-gather + assembly on the communicator's own stream, in alternating buffer sets, so the kernels of batch i + 1
- * run under the collective of batch i (src/dsp/mimo.cpp:121-151: a rank's directions do not depend on the gather), and the
- * kernels themselves alternate between the handle's two compute streams like bflk_power_map_batch_dev_submit's.
+ * run under the collective of batch i (src/dsp/mimo.cpp:121-151: a rank's directions do not depend on the gather).
  * power_all_dev of every batch submitted so far is complete for work enqueued on cuda_stream after
  * bflk_power_map_batch_sharded_dev_join(h, cuda_stream) (asynchronous: it enqueues a wait, the host does not block). */
 int bflk_power_map_batch_sharded_dev_submit(bflk_handle *h, const float *stream_dev, int64_t n_samples, int32_t n_frames,
