@@ -590,6 +590,8 @@ def run_ours(args, c, name):
             step()
         n_bi = min(args.steps, 20)
         bms, _, bdas_ms, bdas_n, _, _ = measure_resident(w, tm, step, n_bi, fl_launch)
+        if not args.no_overlap:      # the kernel's own launch duration: synchronous calls (see above)
+            _, _, bdas_ms, bdas_n, _, _ = measure_resident(w, tm, step_with(w, overlap=False), n_bi, fl_launch)
         bk = w.kernel_info()
         bit_identical = {"value": B * n_bi / (bms / 1e3), "unit": UNIT, "steps": n_bi, "kernel": KERNEL_NAMES.get(bk[0], "?"),
                          "tflops_kernel": fl_launch / (bdas_ms / 1e3 / max(1, bdas_n)) / 1e12 if bdas_n else None,
@@ -687,11 +689,16 @@ def run_ours(args, c, name):
         gstep = step_with(wg)
         for _ in range(3):
             gstep()
-        gms, _, gdas_ms, gdas_n, gpack_ms, _ = measure_resident(wg, tm, gstep, args.steps, 0)
+        gms, _, gdas_ms, gdas_n, gpack_ms, gpack_n = measure_resident(wg, tm, gstep, args.steps, 0)
+        gms_step = gms / args.steps
+        if not args.no_overlap:
+            n_g = max(5, min(args.steps, 20))
+            gms_sync, _, gdas_ms, gdas_n, gpack_ms, gpack_n = measure_resident(wg, tm, step_with(wg, overlap=False), n_g, 0)
+            gms_step = gms_sync / n_g
         g_first, g_count, _, _ = bflk.shard_plan(D, B, world, rank, world)
         grid_shard = {"parallelism": f"{world} direction groups x 1 frame group", "value": B * args.steps / (gms / 1e3), "unit": UNIT,
                       "tflops_kernel": flops_per_map(C, g_count, N) * B / (gdas_ms / 1e3 / max(1, gdas_n)) / 1e12 if gdas_n else None,
-                      "pack_share_of_step": gpack_ms / gms, "same_maps": bool(torch.equal(out_all, ref_maps))}
+                      "pack_share_of_step": gpack_ms / max(1, gpack_n) / gms_step, "same_maps": bool(torch.equal(out_all, ref_maps))}
         wg.close()
 
     # ---- cfg5 (256x256 grid x 4096-sample frames) on all N GPUs, grid sharded N ways, same run ----
