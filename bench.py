@@ -12,6 +12,14 @@ torch.distributed) and a step is one bflk_power_map_batch_sharded_dev call -- th
 `grid_shard`), all-gathers the slices with NCCL and leaves the complete [B][D] maps on every rank.  Total work is fixed
 ("strong" scaling).
 
+The K timed steps run in CONTINUOUS OPERATION, as a live system would: at N = 1 consecutive steps alternate between the
+handle's two compute streams (bflk_power_map_batch_dev_submit; the pack pre-pass of step i + 1 under the kernel of step i),
+at N > 1 the all-gather + assembly of step i run on the communicator's stream under the kernels of step i + 1
+(bflk_power_map_batch_sharded_dev_submit); the join that makes the last maps visible is inside the timed region, and every
+step computes and delivers its own complete maps.  `synchronous_call_value`: the same with one synchronous call per step
+(--no-overlap makes that the headline).  The dominant kernel's OWN launch duration (`roofline.achieved`, the shares of a
+step) is timed in a pass of synchronous calls -- overlapping launches would stretch the event pairs around them.
+
 One JSON line on rank 0.  `value`: maps/s with inputs resident in HBM (automatic kernel = two-FMA form);
 `bit_identical`: the same with the kernel whose delayed sums equal the reference's delay() bit for bit.  `e2e`: through
 the host-buffer C-ABI call (H2D of the batch + D2H of the maps inside the timed region).  `roofline`: the dominant
