@@ -633,7 +633,7 @@ void bflk::comm_release(bflk_handle *h) {
         if (c->ev_computed[k]) cudaEventDestroy(c->ev_computed[k]);
         if (c->ev_gathered[k]) cudaEventDestroy(c->ev_gathered[k]);
     }
-    if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
+    if (c->gather_stream) { cudaStreamSynchronize(c->gather_stream); cudaStreamDestroy(c->gather_stream); }
     c->d_all.release(); c->d_agree.release();
     if (nccl().ok()) {
         if (c->sub && c->sub != c->all) nccl().CommDestroy(c->sub);
