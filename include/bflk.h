@@ -17,6 +17,10 @@
  *   bflk_set_grid_tables            the same LUT supplied by the caller (offsetDelays / fractionalDelays, mimo.h:86-89)
  *   bflk_steer_tables               Particle::steer (src/dsp/particle.cpp:37-49)
  *   bflk_power_map*                 MIMOWorker::update (src/dsp/mimo.cpp:97-151) -> powerdB
+ *   bflk_power_map_batch*_submit / _wait / _join   the same in continuous operation (the reference's worker loop,
+ *                                   src/dsp/worker.h:212-224, calls update() frame after frame): batches overlap their
+ *                                   uploads, pre-passes and collectives with the kernels of their neighbours
+ *   bflk_set_channel_split, bflk_launch_shape   latency shape of one live frame (MIMOWorker::update once per 5.24 ms)
  *   bflk_enable_timing / bflk_kernel_time_ms / bflk_launch_count   (no reference counterpart: measurement hooks)
  *   bflk_miso*                      Particle::steer + Particle::das + Particle::beam
  *                                   (src/dsp/particle.cpp:37-103) as used by MISOWorker::update (miso.cpp:39-46)
